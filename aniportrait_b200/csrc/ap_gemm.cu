@@ -1,0 +1,491 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   out[M, N] = epilogue( A[M, K] * W[N, K]^T )           fp16 operands, fp32 accumulation in TMEM
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier full/empty)
+//   warp 1      MMA issuer    (tcgen05.mma cta_group::1, M=128, N=BN, K=16; accumulators double-buffered in TMEM)
+//   warps 2..5  epilogue      (tcgen05.ld -> +bias, +residual | GEGLU -> fp16 -> global), overlaps next tile's mainloop
+//
+// The A operand is fetched by TMA in one of three addressing modes, so that linear layers, 1x1 convs, 3x3 convs
+// (stride 1 and 2, zero padding via TMA out-of-bounds fill) and channel-concatenated inputs (two K sources) share
+// one mainloop and no im2col / concat buffer is ever materialised:
+//   A_GEMM      2-D map [M, K]            (optionally a second map: K = K1 ++ K2)
+//   A_CONV_S1   4-D map (C, W, H, Nf)     box {64, bw, bh, bn}, tap (ky,kx) -> coordinate shift (kx-1, ky-1)
+//   A_CONV_S2   5-D map (2C, W/2, 2, H/2, Nf) (even/odd pixel phases split out), box {64, bw, 1, bh, bn}
+//
+// Replaces, for the hot path: cuDNN/cuBLAS calls behind InflatedConv3d (reference src/models/resnet.py:10-18),
+// nn.Linear / 1x1 nn.Conv2d in Transformer3DModel (src/models/transformer_3d.py:64-66,93-95), diffusers Attention
+// to_q/k/v/out and FeedForward(GEGLU) (src/models/attention.py:323-361, src/models/motion_module.py:122,144,233).
+#include <stdio.h>
+
+#include "ap_host.h"
+#include "ap_ptx.cuh"
+
+namespace ap {
+
+enum { A_GEMM = 0, A_CONV_S1 = 1, A_CONV_S2 = 2 };
+enum { EPI_LINEAR = 0, EPI_GEGLU = 1 };
+
+struct GemmParams {
+  int M, N;                // output rows; weight rows (N % BN == 0)
+  int num_m_tiles, num_n_tiles, num_kb;
+  int a_mode;
+  int kb_src1, kb_src2;    // 64-wide k-blocks per tap taken from source 1 / source 2
+  // conv geometry (output grid) and tile box
+  int Nf, Ho, Wo;
+  int bw, bh, bn;
+  int tiles_x, tiles_y;
+  int C1;                  // channels of source 1 (A_CONV_S2 merged (phase, channel) coordinate)
+  // epilogue
+  const float* bias;       // [groups, Nout] fp32 or null
+  int bias_group_rows;     // rows sharing one bias row (>= M -> single row)
+  const __half* residual;  // [M, ldr] or null
+  int ldr;
+  __half* out;             // [M, ldo]
+  int ldo;
+  int n_valid;             // columns >= n_valid are not stored
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int MAX_SMEM = 227 * 1024 - 2048;
+  static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    if (p.kb_src2 > 0) tma_prefetch_desc(&tmA2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int kb_per_tap = p.kb_src1 + p.kb_src2;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile % p.num_n_tiles;
+        int n0 = 0, y0 = 0, x0 = 0;
+        if (p.a_mode != A_GEMM) {
+          const int per_frame = p.tiles_x * p.tiles_y;
+          const int tn = m_tile / per_frame;
+          const int rem = m_tile % per_frame;
+          n0 = tn * p.bn;
+          y0 = (rem / p.tiles_x) * p.bh;
+          x0 = (rem % p.tiles_x) * p.bw;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          void* a_dst = smem_a + stage * Cfg::A_BYTES;
+          void* b_dst = smem_b + stage * Cfg::B_BYTES;
+          const int tap = kb / kb_per_tap;
+          const int within = kb % kb_per_tap;
+          const bool second = within >= p.kb_src1;
+          const CUtensorMap* am = second ? &tmA2 : &tmA1;
+          const int c0 = (second ? within - p.kb_src1 : within) * Cfg::BK;
+          if (p.a_mode == A_GEMM) {
+            tma_load_2d(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
+          } else if (p.a_mode == A_CONV_S1) {
+            const int ky = tap / 3, kx = tap % 3;
+            tma_load_4d(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
+          } else {
+            // input pixel = 2*o + k - 1  ->  k=0: (o-1, phase 1), k=1: (o, phase 0), k=2: (o, phase 1)
+            const int ky = tap / 3, kx = tap % 3;
+            const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
+            const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
+            tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
+          }
+          tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in the (>>4) start-address field
+            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are accessible to this warp
+    const int row = lane_group * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile % p.num_n_tiles;
+      // output row of this thread
+      long long m;
+      bool row_ok;
+      if (p.a_mode == A_GEMM) {
+        m = (long long)m_tile * Cfg::BM + row;
+        row_ok = m < p.M;
+      } else {
+        const int per_frame = p.tiles_x * p.tiles_y;
+        const int tn = m_tile / per_frame;
+        const int rem = m_tile % per_frame;
+        const int n = tn * p.bn + row / (p.bh * p.bw);
+        const int y = (rem / p.tiles_x) * p.bh + (row / p.bw) % p.bh;
+        const int x = (rem % p.tiles_x) * p.bw + row % p.bw;
+        row_ok = (n < p.Nf) && (y < p.Ho) && (x < p.Wo);
+        m = ((long long)n * p.Ho + y) * p.Wo + x;
+      }
+      const float* bias_row = nullptr;
+      if (p.bias != nullptr) {
+        const long long g = row_ok ? (m / p.bias_group_rows) : 0;
+        bias_row = p.bias + g * (long long)(EPI == EPI_GEGLU ? p.N : p.N);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(lane_group * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int ncol = n_tile * BN + c * 32;  // column in weight-row space
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (bias_row != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_row + ncol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (EPI == EPI_GEGLU) {
+          // interleaved weights: columns [0,16) = value half, [16,32) = gate half of the same 16 outputs
+          const int ocol = ncol >> 1;
+          if (row_ok) {
+            __half2 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = v[2 * j] * gelu_erf(v[16 + 2 * j]);
+              const float a1 = v[2 * j + 1] * gelu_erf(v[16 + 2 * j + 1]);
+              o[j] = __floats2half2_rn(a0, a1);
+            }
+            __half* dst = p.out + m * p.ldo + ocol;
+            if (ocol + 16 <= p.n_valid && (p.ldo & 7) == 0) {
+              uint4* d4 = reinterpret_cast<uint4*>(dst);
+              d4[0] = *reinterpret_cast<uint4*>(&o[0]);
+              d4[1] = *reinterpret_cast<uint4*>(&o[4]);
+            } else {
+              const __half* oh = reinterpret_cast<const __half*>(o);
+              for (int j = 0; j < 16; ++j)
+                if (ocol + j < p.n_valid) dst[j] = oh[j];
+            }
+          }
+        } else {
+          if (row_ok) {
+            const bool vec_ok = (ncol + 32 <= p.n_valid) && ((p.ldo & 7) == 0);
+            if (p.residual != nullptr) {
+              const __half* rs = p.residual + m * p.ldr + ncol;
+              if (vec_ok && (p.ldr & 7) == 0) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(rs);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u = __ldg(r4 + q);
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    v[q * 8 + 2 * j] += f.x;
+                    v[q * 8 + 2 * j + 1] += f.y;
+                  }
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (ncol + j < p.n_valid) v[j] += __half2float(rs[j]);
+              }
+            }
+            __half* dst = p.out + m * p.ldo + ncol;
+            if (vec_ok) {
+              uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __half2 o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+                d4[q] = *reinterpret_cast<uint4*>(o);
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (ncol + j < p.n_valid) dst[j] = __float2half_rn(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<BN, EPI><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, p);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+static int pick_bn(int N, int forced) {
+  if (forced > 0) return forced;
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  if (N % 32 == 0) return 32;
+  return -1;
+}
+
+static int dispatch(int bn, int epi, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
+                    const GemmParams& p, cudaStream_t stream) {
+#define AP_CASE(BN_)                                                          \
+  case BN_:                                                                   \
+    return epi == EPI_GEGLU ? launch_gemm<BN_, EPI_GEGLU>(a1, a2, b, p, stream) \
+                            : launch_gemm<BN_, EPI_LINEAR>(a1, a2, b, p, stream);
+  switch (bn) {
+    AP_CASE(256)
+    AP_CASE(160)
+    AP_CASE(128)
+    AP_CASE(64)
+    AP_CASE(32)
+    default:
+      return fail(AP_ERR_INVALID, "gemm: unsupported BLOCK_N %d", bn);
+  }
+#undef AP_CASE
+}
+
+static int make_weight_map(CUtensorMap* tm, const void* w, int N, long long K, int bn) {
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t strides[1] = {(uint64_t)K * 2};
+  const uint32_t box[2] = {64, (uint32_t)bn};
+  return encode_tmap(tm, w, 2, dims, strides, box, true);
+}
+
+}  // namespace ap
+
+using namespace ap;
+
+extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2, long long lda2, int K2,
+                           const void* w, long long M, int N, const float* bias, long long bias_group_rows,
+                           const void* residual, long long ldr, void* out, long long ldo, int n_valid, int flags,
+                           int block_n, void* stream) {
+  AP_REQUIRE(a && w && out, "gemm: null pointer");
+  AP_REQUIRE(M > 0 && N > 0 && K1 > 0, "gemm: bad shape M=%lld N=%d K1=%d", M, N, K1);
+  AP_REQUIRE(K1 % 64 == 0 || (a2 == nullptr), "gemm: K1 must be a multiple of 64 when a second source follows");
+  AP_REQUIRE((lda % 8) == 0 && (a2 == nullptr || (lda2 % 8) == 0), "gemm: lda must be a multiple of 8 elements");
+  const int epi = (flags & AP_GEMM_GEGLU) ? EPI_GEGLU : EPI_LINEAR;
+  const int bn = pick_bn(N, block_n);
+  AP_REQUIRE(bn > 0 && N % bn == 0, "gemm: N=%d not tileable (block_n=%d)", N, block_n);
+  const long long K = (long long)K1 + (a2 ? K2 : 0);
+  AP_REQUIRE((K * 2) % 16 == 0, "gemm: K*2 bytes must be a multiple of 16");
+
+  GemmParams p{};
+  p.M = (int)M;
+  p.N = N;
+  p.num_m_tiles = (int)((M + 127) / 128);
+  p.num_n_tiles = N / bn;
+  p.a_mode = A_GEMM;
+  p.kb_src1 = (K1 + 63) / 64;
+  p.kb_src2 = a2 ? (K2 + 63) / 64 : 0;
+  p.num_kb = p.kb_src1 + p.kb_src2;
+  p.bias = bias;
+  p.bias_group_rows = (int)(bias_group_rows > 0 ? (bias_group_rows > 0x7fffffff ? 0x7fffffff : bias_group_rows)
+                                                : 0x7fffffff);
+  p.residual = (const __half*)residual;
+  p.ldr = (int)ldr;
+  p.out = (__half*)out;
+  p.ldo = (int)ldo;
+  const int nout = epi == EPI_GEGLU ? N / 2 : N;
+  p.n_valid = n_valid > 0 ? n_valid : nout;
+
+  CUtensorMap tmA1, tmA2, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = encode_tmap(&tmA1, a, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  if (a2) {
+    const uint64_t dims[2] = {(uint64_t)K2, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)lda2 * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = encode_tmap(&tmA2, a2, 2, dims, strides, box, true);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA1;
+  }
+  int rc = make_weight_map(&tmB, w, N, K, bn);
+  if (rc) return rc;
+  return dispatch(bn, epi, tmA1, tmA2, tmB, p, (cudaStream_t)stream);
+}
+
+// 3x3 convolution, padding 1, stride 1 or 2, NHWC fp16, optional channel-concatenated second input.
+extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int H, int W, int stride,
+                                   const void* w, int Cout, const float* bias, long long bias_group_rows,
+                                   const void* residual, void* out, long long ldo, int n_valid, int block_n,
+                                   void* stream) {
+  AP_REQUIRE(x && w && out, "conv3x3: null pointer");
+  AP_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
+  AP_REQUIRE(C1 % 64 == 0 && (x2 == nullptr || C2 % 64 == 0), "conv3x3: channels must be multiples of 64 (pad)");
+  AP_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "conv3x3: stride 2 needs even H, W");
+  const int Ho = H / stride, Wo = W / stride;
+  const int bn_ = pick_bn(Cout, block_n);
+  AP_REQUIRE(bn_ > 0 && Cout % bn_ == 0, "conv3x3: Cout=%d not tileable", Cout);
+
+  // tile box: bw x bh x bn output pixels = 128 rows, bw | Wo, bh | Ho (powers of two)
+  auto pow2_div = [](int v, int cap) { int d = 1; while (d * 2 <= cap && v % (d * 2) == 0) d *= 2; return d; };
+  const int bw = pow2_div(Wo, 128);
+  const int bh = pow2_div(Ho, 128 / bw);
+  const int bnf = 128 / (bw * bh);
+
+  GemmParams p{};
+  p.Nf = Nf; p.Ho = Ho; p.Wo = Wo;
+  p.bw = bw; p.bh = bh; p.bn = bnf;
+  p.tiles_x = Wo / bw;
+  p.tiles_y = Ho / bh;
+  p.M = Nf * Ho * Wo;
+  p.N = Cout;
+  p.num_m_tiles = ((Nf + bnf - 1) / bnf) * p.tiles_x * p.tiles_y;
+  p.num_n_tiles = Cout / bn_;
+  p.a_mode = stride == 1 ? A_CONV_S1 : A_CONV_S2;
+  p.kb_src1 = C1 / 64;
+  p.kb_src2 = x2 ? C2 / 64 : 0;
+  p.num_kb = 9 * (p.kb_src1 + p.kb_src2);
+  p.C1 = C1;
+  p.bias = bias;
+  p.bias_group_rows = (int)(bias_group_rows > 0 ? (bias_group_rows > 0x7fffffff ? 0x7fffffff : bias_group_rows)
+                                                : 0x7fffffff);
+  p.residual = (const __half*)residual;
+  p.ldr = (int)ldo;
+  p.out = (__half*)out;
+  p.ldo = (int)ldo;
+  p.n_valid = n_valid > 0 ? n_valid : Cout;
+
+  auto make_act_map = [&](CUtensorMap* tm, const void* base, int C) -> int {
+    if (stride == 1) {
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)Nf};
+      const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+      const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnf};
+      return encode_tmap(tm, base, 4, dims, strides, box, true);
+    }
+    // (phase_x * C + c, W/2, phase_y, H/2, Nf)
+    const uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)Nf};
+    const uint64_t strides[4] = {(uint64_t)2 * C * 2, (uint64_t)W * C * 2, (uint64_t)2 * W * C * 2,
+                                 (uint64_t)H * W * C * 2};
+    const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bnf};
+    return encode_tmap(tm, base, 5, dims, strides, box, true);
+  };
+  CUtensorMap tmA1, tmA2, tmB;
+  int rc = make_act_map(&tmA1, x, C1);
+  if (rc) return rc;
+  if (x2) {
+    rc = make_act_map(&tmA2, x2, C2);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA1;
+  }
+  rc = make_weight_map(&tmB, w, Cout, 9ll * (C1 + (x2 ? C2 : 0)), bn_);
+  if (rc) return rc;
+  return dispatch(bn_, EPI_LINEAR, tmA1, tmA2, tmB, p, (cudaStream_t)stream);
+}
