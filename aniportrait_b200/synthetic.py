@@ -1,0 +1,44 @@
+"""Seeded synthetic weights / inputs (there are no checkpoints or datasets offline). SURVEY.md §8d recipe: normal(0, 0.02)
+weights, zero biases, unit norm scales, PoseGuider scale 2, sinusoidal PE buffers as computed."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def randomize_state_dict(sd: dict, seed: int = 0, std: float = 0.02) -> dict:
+    """Deterministically re-initialise a state dict in place (CPU generator; name order = dict order)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = {}
+    for name, t in sd.items():
+        if name.endswith(".pe"):  # positional-encoding buffers keep their analytic values
+            out[name] = t
+            continue
+        if not t.is_floating_point():
+            out[name] = t
+            continue
+        leaf = name.rsplit(".", 1)[-1]
+        is_norm = any(k in name for k in (".norm", "norm1", "norm2", "norm3", "ff_norm", "norms.", "group_norm",
+                                          "conv_norm_out"))
+        is_bn = t.dim() == 1 and ("conv_layers" in name)
+        if name == "scale":
+            v = torch.full_like(t, 2.0)
+        elif "running_mean" in name:
+            v = torch.zeros_like(t)
+        elif "running_var" in name:
+            v = torch.ones_like(t)
+        elif (is_norm or (is_bn and leaf == "weight" and t.dim() == 1 and _is_bn_name(name, sd))) and leaf == "weight":
+            v = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        elif leaf == "bias":
+            v = 0.02 * torch.randn(t.shape, generator=g)
+        else:
+            fan_in = t[0].numel() if t.dim() > 1 else t.numel()
+            v = torch.randn(t.shape, generator=g) * min(std * 2.5, 1.0 / math.sqrt(max(fan_in, 1)))
+        out[name] = v.to(t.dtype)
+    return out
+
+
+def _is_bn_name(name, sd):
+    base = name.rsplit(".", 1)[0]
+    return (base + ".running_mean") in sd

@@ -1,0 +1,131 @@
+"""Pins the CPU oracle (oracle/functional.py) against the UNMODIFIED reference wiring imported from /root/reference
+through oracle/diffusers_shim. Runs only where the reference tree exists (the authoring container); the same
+comparison at full SD1.5 width is frozen into tests/golden/ by oracle/make_golden.py for the GPU box."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import functional as OF  # noqa: E402
+from oracle import ref_import  # noqa: E402
+from aniportrait_b200.synthetic import randomize_state_dict  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+SMALL = (64, 128, 256, 256)
+CFG_SMALL = dict(OF.SD15, block_out_channels=SMALL)
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def _load(model, seed):
+    sd = randomize_state_dict(model.state_dict(), seed=seed)
+    model.load_state_dict(sd)
+    return sd
+
+
+@pytest.fixture(scope="module")
+def nets():
+    torch.manual_seed(0)
+    unet3d = ref_import.build_unet3d(SMALL)
+    unet2d = ref_import.build_unet2d(SMALL)
+    sd3 = _load(unet3d, 1)
+    sd2 = _load(unet2d, 2)
+    return unet3d, sd3, unet2d, sd2
+
+
+def test_unet3d_plain_forward(nets):
+    """No reference attention: UNet3DConditionModel.forward vs oracle.unet3d_forward."""
+    unet3d, sd3, _, _ = nets
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 3, 16, 16, generator=g)
+    ehs = torch.randn(2, 1, 768, generator=g)
+    pose = [torch.randn(2, c, 3, s, s, generator=g) for c, s in [(64, 16), (64, 8), (128, 4), (256, 2), (256, 2)]]
+    with torch.no_grad():
+        ref = unet3d(x, torch.tensor(500), encoder_hidden_states=ehs, pose_cond_fea=pose, return_dict=False)[0]
+        ours = OF.unet3d_forward(sd3, x, 500, ehs, pose, banks=None, cfg=False, c=CFG_SMALL)
+    assert rel_l2(ours, ref) < 1e-5
+
+
+def test_reference_attention_read_write(nets):
+    """Writer/reader through ReferenceAttentionControl (CFG on) vs oracle banks + read-mode blocks."""
+    unet3d, sd3, unet2d, sd2 = nets
+    ref_import.activate()
+    from src.models.mutual_self_attention import ReferenceAttentionControl
+    g = torch.Generator().manual_seed(4)
+    Fr = 16  # the reference hard-codes a 16-frames-per-branch uc_mask (mutual_self_attention.py:77-85)
+    x = torch.randn(1, 4, Fr, 8, 8, generator=g).repeat(2, 1, 1, 1, 1)
+    clip = torch.randn(1, 768, generator=g)
+    ehs = torch.cat([torch.zeros_like(clip), clip], 0).unsqueeze(1)
+    ref_lat = torch.randn(1, 4, 8, 8, generator=g)
+    writer = ReferenceAttentionControl(unet2d, do_classifier_free_guidance=True, mode="write", batch_size=1,
+                                       fusion_blocks="full")
+    reader = ReferenceAttentionControl(unet3d, do_classifier_free_guidance=True, mode="read", batch_size=1,
+                                       fusion_blocks="full")
+    try:
+        with torch.no_grad():
+            unet2d(ref_lat.repeat(2, 1, 1, 1), torch.zeros((), dtype=torch.long), encoder_hidden_states=ehs,
+                   return_dict=False)
+            reader.update(writer, dtype=torch.float32)
+            ref = unet3d(x, torch.tensor(959), encoder_hidden_states=ehs, return_dict=False)[0]
+            banks = OF.reference_unet_banks(sd2, ref_lat.repeat(2, 1, 1, 1), ehs, c=CFG_SMALL)
+            ours = OF.unet3d_forward(sd3, x, 959, ehs, None, banks=OF.pair_banks(banks), cfg=True, c=CFG_SMALL)
+    finally:
+        reader.clear()
+        writer.clear()
+        for m in list(unet2d.modules()) + list(unet3d.modules()):
+            if hasattr(m, "_original_inner_forward"):
+                m.forward = m._original_inner_forward
+    assert len(banks) == 16
+    assert rel_l2(ours, ref) < 1e-5
+
+
+def test_pose_guider():
+    pg = ref_import.build_pose_guider(64)
+    sd = _load(pg, 5)
+    pg.train()  # the scripts never call .eval(): BatchNorm uses batch statistics
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 3, 2, 64, 64, generator=g)
+    with torch.no_grad():
+        ref = pg(x, torch.randn(1, 3, 64, 64, generator=g))
+        ours = OF.pose_guider_forward(sd, x, 64)
+    for a, b in zip(ours, ref):
+        assert a.shape == b.shape
+        assert rel_l2(a, b) < 1e-5
+
+
+def test_ddim_and_windows():
+    ref_import.activate()
+    from diffusers.schedulers import DDIMScheduler
+    from src.pipelines.context import uniform
+    s = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+                      prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+    s.set_timesteps(25)
+    o = OF.DDIM()
+    assert s.timesteps.tolist() == o.timesteps(25)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 4, 2, 8, 8, generator=g)
+    v = torch.randn(1, 4, 2, 8, 8, generator=g)
+    for t in (999, 479, 39):
+        assert rel_l2(o.step(v, t, x, 25), s.step(v, t, x).prev_sample) < 1e-6
+    for n in (4, 16, 24, 128):
+        assert list(uniform(0, 25, n, 16, 1, 4)) == OF.context_windows(n, 16, 4)
+
+
+def test_vae_decode():
+    ref_import.activate()
+    from diffusers import AutoencoderKL
+    vae = AutoencoderKL(block_out_channels=(32, 64, 128, 128))
+    sd = _load(vae, 8)
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(2, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        ref = vae.decode(z).sample
+        ours = OF.vae_decode(sd, z)
+    assert rel_l2(ours, ref) < 1e-5
