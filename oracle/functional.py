@@ -155,7 +155,7 @@ def motion_module(sd, p, x, video_length, heads=8, groups=32):
 
 # ------------------------------------------------------------------------------------------------ UNets
 def _time_embed(sd, t, batch, dtype):
-    temb = timestep_embedding(t.expand(batch)).to(dtype)
+    temb = timestep_embedding(t.expand(batch), sd["time_embedding.linear_1.weight"].shape[1]).to(dtype)
     temb = linear(sd, "time_embedding.linear_1", temb)
     return linear(sd, "time_embedding.linear_2", F.silu(temb))
 
@@ -272,10 +272,8 @@ def pair_banks(banks):
 def _bn_train(sd, p, x, eps=1e-5):
     """nn.BatchNorm2d in TRAIN mode (the scripts never call .eval(): scripts/pose2vid.py:102-110): batch statistics,
     biased variance (src/models/pose_guider.py:19-89)."""
-    mean = x.mean(dim=(0, 2, 3), keepdim=True)
-    var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
-    y = (x - mean) / torch.sqrt(var + eps)
-    return y * sd[p + ".weight"][None, :, None, None] + sd[p + ".bias"][None, :, None, None]
+    # y = (x - mean_batch) / sqrt(var_batch_biased + eps) * gamma + beta
+    return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], training=True, momentum=0.0, eps=eps)
 
 
 def pose_guider_forward(sd, x, c0=320):

@@ -91,9 +91,9 @@ def test_pose_guider():
     sd = _load(pg, 5)
     pg.train()  # the scripts never call .eval(): BatchNorm uses batch statistics
     g = torch.Generator().manual_seed(6)
-    x = torch.randn(2, 3, 2, 64, 64, generator=g)
+    x = torch.randn(2, 3, 2, 128, 128, generator=g)
     with torch.no_grad():
-        ref = pg(x, torch.randn(1, 3, 64, 64, generator=g))
+        ref = pg(x, torch.randn(1, 3, 128, 128, generator=g))
         ours = OF.pose_guider_forward(sd, x, 64)
     for a, b in zip(ours, ref):
         assert a.shape == b.shape
