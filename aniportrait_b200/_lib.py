@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_float, POINTER
+from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_float, POINTER  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaniportrait_b200.so")

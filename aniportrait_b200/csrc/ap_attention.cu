@@ -1,0 +1,436 @@
+// Fused spatial self / reference attention for sm_100a (flash-style, tcgen05 + TMEM + TMA).
+//
+//   O[f, h] = softmax( Q[f,h] . [K_own[f,h] ; K_bank[h]]^T * scale ) . [V_own[f,h] ; V_bank[h]]
+//
+// One launch covers every frame of a UNet call: frames before `first_bank_frame` (the unconditional CFG branch)
+// attend to their own N tokens only, the others to 2N keys (own tokens followed by the ReferenceNet bank, whose K/V
+// were projected once per video and are read in place: no `bank.repeat(F)` / `torch.cat` copy, no discarded
+// reference-attention for the unconditional half, no CPU-mask scatter).
+//
+// Replaces diffusers Attention/AttnProcessor2_0 -> F.scaled_dot_product_attention as driven by the patched block
+// forward of ReferenceAttentionControl (reference src/models/mutual_self_attention.py:147-186; plain blocks
+// src/models/attention.py:323-330, write mode :137-146; PoseGuider's self-attention src/models/pose_guider.py:86-89).
+//
+// Persistent CTAs over (frame, head, 128-query tile) work units; 6 warps:
+//   warp 0     TMA producer: Q tile once per unit, K/V tiles through an mbarrier ring (own rows, then bank rows)
+//   warp 1     MMA issuer:   S = Q.K^T (accumulator double-buffered in TMEM), O += P.V (P from smem, V MN-major)
+//   warps 2-5  softmax + epilogue: thread = query row; S row held in registers; base-2 online softmax with lazy
+//              (thresholded) rescaling of the TMEM-resident O; P written to 128B-swizzled smem as the next A operand.
+// Head dim d is zero-padded to DPAD in {64,128,192} by the QKV projection (padded weight rows), so every operand slab
+// is a clean 64-column / 128-byte swizzle atom.
+#include <stdio.h>
+
+#include "ap_host.h"
+#include "ap_ptx.cuh"
+
+namespace ap {
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnParams {
+  int n_frames, tokens, heads, head_dim;
+  int bank_tokens;        // 0 = no bank
+  int first_bank_frame;   // frames >= this attend to the bank as well
+  int frames_per_bank;    // bank index = (frame - first_bank_frame) / frames_per_bank
+  int m_tiles;            // ceil(tokens / 128)
+  int num_units;          // n_frames * heads * m_tiles
+  float scale_log2;       // softmax scale * log2(e)
+  __half* out;
+  long long ldo;
+};
+
+template <int DPAD, int BN>
+struct AttnCfg {
+  static constexpr int SLABS = DPAD / 64;
+  static constexpr int Q_BYTES = 128 * DPAD * 2;
+  static constexpr int K_BYTES = BN * DPAD * 2;
+  static constexpr int P_BYTES = 128 * BN * 2;
+  static constexpr int KV_STAGE = 2 * K_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 2048 - Q_BYTES - P_BYTES;
+  static constexpr int STAGES_RAW = BUDGET / KV_STAGE;
+  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + STAGES * KV_STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_S0 = 0, TMEM_S1 = 128, TMEM_O = 256;
+  static_assert(STAGES >= 2, "need at least a double-buffered K/V ring");
+  static_assert(DPAD % 64 == 0 && DPAD <= 256 && (BN == 64 || BN == 128), "tile config");
+};
+
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: stale row maxima keep P <= 2^8 (fine for fp16 P, fp32 O)
+
+template <int DPAD, int BN>
+__global__ void __launch_bounds__(192, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
+                 const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
+  using Cfg = AttnCfg<DPAD, BN>;
+  constexpr int ST = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_p = smem_q + Cfg::Q_BYTES;
+  uint8_t* smem_kv = smem_p + Cfg::P_BYTES;  // stage s: K at s*KV_STAGE, V at s*KV_STAGE + K_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ST * Cfg::KV_STAGE);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;            // [ST]
+  uint64_t* v_full = k_full + ST;         // [ST]
+  uint64_t* kv_empty = v_full + ST;       // [ST]
+  uint64_t* s_full = kv_empty + ST;       // [2]
+  uint64_t* s_empty = s_full + 2;         // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* pv_done = p_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int own_tiles = (p.tokens + BN - 1) / BN;
+  const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
+  const int units_per_frame = p.heads * p.m_tiles;
+
+  // unit -> (frame, head, m_tile); frames with a bank (the heavy ones) are scheduled first
+  auto decode = [&](int unit, int& frame, int& head, int& m_tile, int& T) {
+    const int fk = unit / units_per_frame;
+    const int rem = unit % units_per_frame;
+    frame = (fk + p.first_bank_frame) % p.n_frames;
+    head = rem / p.m_tiles;
+    m_tile = rem % p.m_tiles;
+    const bool has_bank = p.bank_tokens > 0 && frame >= p.first_bank_frame;
+    T = own_tiles + (has_bank ? bank_tiles : 0);
+  };
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t g = 0;   // global K/V tile counter
+      uint32_t uc = 0;  // unit counter
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+        int frame, head, m_tile, T;
+        decode(unit, frame, head, m_tile, T);
+        mbar_wait(q_empty, (uc & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+        for (int s = 0; s < Cfg::SLABS; ++s)
+          tma_load_2d(&tmQ, q_full, smem_q + s * (128 * 128), head * DPAD + s * 64,
+                      frame * p.tokens + m_tile * 128);
+        const int bank_idx = (frame - p.first_bank_frame) / p.frames_per_bank;
+        for (int j = 0; j < T; ++j, ++g) {
+          const int stage = g % ST;
+          const uint32_t ph = (g / ST) & 1;
+          mbar_wait(&kv_empty[stage], ph ^ 1);
+          const bool own = j < own_tiles;
+          const CUtensorMap* mk = own ? &tmK : &tmBK;
+          const CUtensorMap* mv = own ? &tmV : &tmBV;
+          const int row = own ? frame * p.tokens + j * BN : bank_idx * p.bank_tokens + (j - own_tiles) * BN;
+          uint8_t* kd = smem_kv + stage * Cfg::KV_STAGE;
+          uint8_t* vd = kd + Cfg::K_BYTES;
+          mbar_arrive_expect_tx(&k_full[stage], Cfg::K_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_2d(mk, &k_full[stage], kd + s * (BN * 128), head * DPAD + s * 64, row);
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::K_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_2d(mv, &v_full[stage], vd + s * (BN * 128), head * DPAD + s * 64, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);  // B (= V) is MN-major
+      uint32_t g = 0, uc = 0;
+      auto issue_qk = [&](uint32_t gi, bool last_of_unit) {
+        const int sbuf = gi & 1;
+        const int stage = gi % ST;
+        mbar_wait(&s_empty[sbuf], ((gi >> 1) & 1) ^ 1);
+        mbar_wait(&k_full[stage], (gi / ST) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (sbuf ? Cfg::TMEM_S1 : Cfg::TMEM_S0);
+        const uint32_t qa = smem_u32(smem_q);
+        const uint32_t ka = smem_u32(smem_kv + stage * Cfg::KV_STAGE);
+#pragma unroll
+        for (int kk = 0; kk < DPAD / 16; ++kk) {
+          const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
+          const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
+          umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
+        }
+        umma_commit(&s_full[sbuf]);
+        if (last_of_unit) umma_commit(q_empty);
+      };
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+        int frame, head, m_tile, T;
+        decode(unit, frame, head, m_tile, T);
+        mbar_wait(q_full, uc & 1);
+        for (int j = 0; j < T; ++j, ++g) {
+          if (j == 0) issue_qk(g, T == 1);
+          if (j + 1 < T) issue_qk(g + 1, j + 2 == T);
+          const int stage = g % ST;
+          mbar_wait(p_full, g & 1);
+          mbar_wait(&v_full[stage], (g / ST) & 1);
+          tc_fence_after();
+          const uint32_t pa = smem_u32(smem_p);
+          const uint32_t va = smem_u32(smem_kv + stage * Cfg::KV_STAGE + Cfg::K_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint64_t da = umma_desc_k_sw128(pa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
+            const uint64_t db = umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128);
+            umma_f16_ss(tmem_base + Cfg::TMEM_O, da, db, idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(&kv_empty[stage]);
+          umma_commit(pv_done);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------------- softmax + epilogue
+    const int lane_group = warp & 3;
+    const int row = lane_group * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(lane_group * 32) << 16;
+    uint32_t g = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int frame, head, m_tile, T;
+      decode(unit, frame, head, m_tile, T);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < T; ++j, ++g) {
+        const int sbuf = g & 1;
+        mbar_wait(&s_full[sbuf], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t sr[BN];
+        const uint32_t t_s = tmem_base + (sbuf ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sbuf]);
+
+        // valid keys in this tile
+        const bool own = j < own_tiles;
+        const int jj = own ? j : j - own_tiles;
+        const int ntok = own ? p.tokens : p.bank_tokens;
+        const int valid = min(BN, ntok - jj * BN);
+        float tmax = -INFINITY;
+        if (valid == BN) {
+#pragma unroll
+          for (int i = 0; i < BN; ++i) tmax = fmaxf(tmax, __uint_as_float(sr[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
+            tmax = fmaxf(tmax, __uint_as_float(sr[i]));
+          }
+        }
+        tmax *= p.scale_log2;
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_run = tmax;
+        } else if (tmax > m_run + kRescaleThreshold) {
+          alpha = fast_exp2(m_run - tmax);
+          m_run = tmax;
+          need = true;
+        }
+        const bool warp_need = __any_sync(0xffffffffu, need);
+        l_run *= alpha;
+
+        // P = exp2(S*c - m), packed to fp16 pairs; row sum in fp32
+        uint32_t pk[BN / 2];
+        float lsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < BN; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
+          lsum += p0 + p1;
+          const __half2 h = __floats2half2_rn(p0, p1);
+          pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        l_run += lsum;
+
+        // previous P.V must have completed before P is overwritten / O is rescaled
+        if (g > 0) mbar_wait(pv_done, (g - 1) & 1);
+        if (warp_need) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DPAD / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld_32x32b_x32(tmem_base + Cfg::TMEM_O + t_lane + c * 32, orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_base + Cfg::TMEM_O + t_lane + c * 32, orr);
+          }
+          tmem_st_wait();
+        }
+        // P -> smem (K-major, 128B swizzle: 16B chunk index XOR (row & 7))
+#pragma unroll
+        for (int c = 0; c < BN / 8; ++c) {
+          const int atom = c >> 3, cc = c & 7;
+          uint4 val = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4*>(smem_p + atom * (128 * 128) + row * 128 + ((cc ^ (row & 7)) << 4)) = val;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ------------------------------------------------------------------ epilogue: O / l -> fp16 -> global
+      mbar_wait(pv_done, (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const int q_idx = m_tile * 128 + row;
+      const bool row_ok = q_idx < p.tokens;
+      __half* dst = p.out + ((long long)frame * p.tokens + q_idx) * p.ldo + head * p.head_dim;
+#pragma unroll 1
+      for (int c = 0; c < DPAD / 32; ++c) {
+        if (c * 32 >= p.head_dim) break;
+        uint32_t orr[32];
+        tmem_ld_32x32b_x32(tmem_base + Cfg::TMEM_O + t_lane + c * 32, orr);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c * 32 + q * 8 < p.head_dim) {
+              __half2 o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = __floats2half2_rn(__uint_as_float(orr[q * 8 + 2 * i]) * inv_l,
+                                         __uint_as_float(orr[q * 8 + 2 * i + 1]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = *reinterpret_cast<uint4*>(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int DPAD, int BN>
+static int launch_attention(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
+  using Cfg = AttnCfg<DPAD, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
+  attention_kernel<DPAD, BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+}  // namespace ap
+
+using namespace ap;
+
+extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, long long ld_qkv, const void* bank_k,
+                                const void* bank_v, long long ld_bank, int bank_tokens, int n_banks, int n_frames,
+                                int tokens, int heads, int head_dim, int dpad, int first_bank_frame,
+                                int frames_per_bank, float scale, void* out, long long ldo, void* stream) {
+  AP_REQUIRE(q && k && v && out, "attention: null pointer");
+  AP_REQUIRE(dpad == 64 || dpad == 128 || dpad == 192, "attention: dpad must be 64/128/192 (got %d)", dpad);
+  AP_REQUIRE(head_dim % 8 == 0 && head_dim <= dpad, "attention: head_dim %d must be a multiple of 8 and <= dpad", head_dim);
+  AP_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8 elements");
+  AP_REQUIRE(n_frames > 0 && tokens > 0 && heads > 0, "attention: bad shape");
+  const bool has_bank = bank_k != nullptr && bank_tokens > 0;
+  AP_REQUIRE(!has_bank || (bank_v && frames_per_bank > 0 && first_bank_frame >= 0 && n_banks > 0),
+             "attention: bad bank arguments");
+  const int bn = dpad == 192 ? 64 : 128;
+
+  AttnParams p{};
+  p.n_frames = n_frames;
+  p.tokens = tokens;
+  p.heads = heads;
+  p.head_dim = head_dim;
+  p.bank_tokens = has_bank ? bank_tokens : 0;
+  p.first_bank_frame = has_bank ? first_bank_frame : 0;
+  p.frames_per_bank = has_bank ? frames_per_bank : 1;
+  p.m_tiles = (tokens + 127) / 128;
+  p.num_units = n_frames * heads * p.m_tiles;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = (__half*)out;
+  p.ldo = ldo;
+  if (has_bank) {
+    const int max_bank = (n_frames - 1 - first_bank_frame) / frames_per_bank;
+    AP_REQUIRE(first_bank_frame >= n_frames || max_bank < n_banks, "attention: bank index out of range");
+  }
+
+  CUtensorMap maps[5];
+  const uint64_t cols = (uint64_t)heads * dpad;
+  auto mk = [&](CUtensorMap* tm, const void* base, uint64_t rows, long long ld, uint32_t box_rows) -> int {
+    const uint64_t dims[2] = {cols, rows};
+    const uint64_t strides[1] = {(uint64_t)ld * 2};
+    const uint32_t box[2] = {64, box_rows};
+    return encode_tmap(tm, base, 2, dims, strides, box, true);
+  };
+  int rc;
+  const uint64_t rows = (uint64_t)n_frames * tokens;
+  if ((rc = mk(&maps[0], q, rows, ld_qkv, 128))) return rc;
+  if ((rc = mk(&maps[1], k, rows, ld_qkv, bn))) return rc;
+  if ((rc = mk(&maps[2], v, rows, ld_qkv, bn))) return rc;
+  if (has_bank) {
+    const uint64_t brows = (uint64_t)n_banks * bank_tokens;
+    if ((rc = mk(&maps[3], bank_k, brows, ld_bank, bn))) return rc;
+    if ((rc = mk(&maps[4], bank_v, brows, ld_bank, bn))) return rc;
+  } else {
+    maps[3] = maps[1];
+    maps[4] = maps[2];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dpad == 64) return launch_attention<64, 128>(maps, p, st);
+  if (dpad == 128) return launch_attention<128, 128>(maps, p, st);
+  return launch_attention<192, 64>(maps, p, st);
+}

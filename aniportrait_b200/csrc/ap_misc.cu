@@ -1,0 +1,365 @@
+// Temporal (frame-axis) attention core and small HBM-bound elementwise / layout kernels of the hot path.
+#include "ap_host.h"
+
+namespace ap {
+
+// ---------------------------------------------------------------------------------------------------------
+// Temporal self-attention core of the motion module: for every (batch b, spatial position p, head h) a softmax
+// over the F frames of the window (F <= 32). Reads q/k/v straight out of the fused projection buffer
+// [B*F*N, 3C] (token row = (b*F + f)*N + p) and writes [B*F*N, C] in the same token order, i.e. the two
+// "(b f) d c <-> (b d) f c" rearranges of the reference (src/models/motion_module.py:359-386) are pure index math.
+// Block = 8 warps = 8 heads of a group of positions (so whole 3C-wide token rows are consumed by one block);
+// lane = (position sub-index, query frame i). K then V are staged through shared memory in channel chunks.
+// ---------------------------------------------------------------------------------------------------------
+template <int FP>  // frames padded to a power of two: 4, 8, 16, 32
+__global__ void __launch_bounds__(256)
+temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int B,
+                     int F, int N, int C, int heads, int CH, float scale) {
+  constexpr int PW = 32 / FP;  // positions per warp
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int d = C / heads;
+  const int head = warp % heads;
+  const int sub = lane / FP;
+  const int i = lane % FP;
+  const long long pos_group = blockIdx.x;              // over B * ceil(N / PW)
+  const int groups_per_b = (N + PW - 1) / PW;
+  const int b = (int)(pos_group / groups_per_b);
+  const int p = (int)(pos_group % groups_per_b) * PW + sub;
+  const bool active = (i < F) && (p < N) && (warp < heads);
+  extern __shared__ __align__(16) uint8_t tsm[];
+  // per warp: PW * FP rows x CH halves
+  __half* stage = reinterpret_cast<__half*>(tsm) + (size_t)warp * PW * FP * CH;
+  const long long row = ((long long)(b * F + (i < F ? i : 0))) * N + (p < N ? p : 0);
+  const __half* qrow = qkv + row * ld + head * d;
+  const __half* krow = qrow + C;
+  const __half* vrow = qrow + 2 * C;
+  float s[FP];
+#pragma unroll
+  for (int j = 0; j < FP; ++j) s[j] = 0.f;
+  const int vec = CH / 8;
+  for (int c0 = 0; c0 < d; c0 += CH) {
+    // stage this lane's K row chunk
+    if (active) {
+      for (int u = 0; u < vec; ++u)
+        *reinterpret_cast<uint4*>(stage + (sub * FP + i) * CH + u * 8) =
+            __ldg(reinterpret_cast<const uint4*>(krow + c0 + u * 8));
+    }
+    __syncwarp();
+    if (active) {
+      for (int u = 0; u < vec; ++u) {
+        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(qrow + c0 + u * 8));
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qu);
+        float2 qf[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) qf[t] = __half22float2(q2[t]);
+#pragma unroll
+        for (int j = 0; j < FP; ++j) {
+          if (j < F) {
+            const uint4 ku = *reinterpret_cast<const uint4*>(stage + (sub * FP + j) * CH + u * 8);
+            const __half2* k2 = reinterpret_cast<const __half2*>(&ku);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 kf = __half22float2(k2[t]);
+              s[j] = fmaf(qf[t].x, kf.x, s[j]);
+              s[j] = fmaf(qf[t].y, kf.y, s[j]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < FP; ++j)
+    if (j < F) mx = fmaxf(mx, s[j] * scale);
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < FP; ++j) {
+    s[j] = (j < F) ? __expf(s[j] * scale - mx) : 0.f;
+    l += s[j];
+  }
+  const float inv_l = 1.f / l;
+  __half* orow = out + row * ldo + head * d;
+  for (int c0 = 0; c0 < d; c0 += CH) {
+    if (active) {
+      for (int u = 0; u < vec; ++u)
+        *reinterpret_cast<uint4*>(stage + (sub * FP + i) * CH + u * 8) =
+            __ldg(reinterpret_cast<const uint4*>(vrow + c0 + u * 8));
+    }
+    __syncwarp();
+    if (active) {
+      for (int u = 0; u < vec; ++u) {
+        float acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+#pragma unroll
+        for (int j = 0; j < FP; ++j) {
+          if (j < F) {
+            const uint4 vu = *reinterpret_cast<const uint4*>(stage + (sub * FP + j) * CH + u * 8);
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vu);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 vf = __half22float2(v2[t]);
+              acc[2 * t] = fmaf(s[j], vf.x, acc[2 * t]);
+              acc[2 * t + 1] = fmaf(s[j], vf.y, acc[2 * t + 1]);
+            }
+          }
+        }
+        __half2 o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv_l, acc[2 * t + 1] * inv_l);
+        *reinterpret_cast<uint4*>(orow + c0 + u * 8) = *reinterpret_cast<uint4*>(o);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// elementwise / layout helpers (16-byte vectorised)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
+                           long long nvec) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; idx < nvec; idx += stride) {
+    const uint4 x = __ldg(a + idx), y = __ldg(b + idx);
+    uint4 r;
+    const __half2* x2 = reinterpret_cast<const __half2*>(&x);
+    const __half2* y2 = reinterpret_cast<const __half2*>(&y);
+    __half2* r2 = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fx = __half22float2(x2[t]), fy = __half22float2(y2[t]);
+      r2[t] = __floats2half2_rn(fx.x + fy.x, fx.y + fy.y);
+    }
+    o[idx] = r;
+  }
+}
+
+__global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) {
+    const float v = __half2float(x[idx]);
+    y[idx] = __float2half_rn(v / (1.f + __expf(-v)));
+  }
+}
+
+// nearest-neighbour 2x upsample, channels-last: out[n, y, x, :] = in[n, y/2, x/2, :]
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int Nf, int H, int W,
+                                  int cvec) {
+  const long long total = (long long)Nf * 2 * H * 2 * W * cvec;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    const int c = (int)(idx % cvec);
+    long long r = idx / cvec;
+    const int x = (int)(r % (2 * W));
+    r /= 2 * W;
+    const int y = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    out[idx] = __ldg(in + (((long long)n * H + (y >> 1)) * W + (x >> 1)) * cvec + c);
+  }
+}
+
+// [B, C, F, H, W] (reference layout) -> [(b f), H, W, Cpad] channels-last, zero padded channels
+__global__ void ncfhw_to_nhwc_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int F,
+                                     int HW, int Cpad) {
+  const long long total = (long long)B * F * HW * Cpad;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    const int c = (int)(idx % Cpad);
+    long long r = idx / Cpad;
+    const int px = (int)(r % HW);
+    r /= HW;
+    const int f = (int)(r % F);
+    const int b = (int)(r / F);
+    out[idx] = c < C ? in[(((long long)b * C + c) * F + f) * HW + px] : __float2half(0.f);
+  }
+}
+
+// [(b f), HW, ld] channels-last (first C channels) -> [B, C, F, H, W]
+__global__ void nhwc_to_ncfhw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int F,
+                                     int HW, int ld) {
+  const long long total = (long long)B * C * F * HW;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    const int px = (int)(idx % HW);
+    long long r = idx / HW;
+    const int f = (int)(r % F);
+    r /= F;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    out[idx] = in[(((long long)b * F + f) * HW + px) * ld + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Denoising-loop elementwise ops (reference src/pipelines/pipeline_pose2vid_long.py:521-559)
+// latents: fp16 [L, HW, 4] channels-last master copy.
+// ---------------------------------------------------------------------------------------------------------
+// UNet input for one window: out[(b, f), px, 0..Cpad) = latents[idx[f], px, 0..4) duplicated over `dup` CFG branches
+__global__ void gather_window_kernel(const __half* __restrict__ lat, const int* __restrict__ idx, __half* __restrict__ out,
+                                     int dup, int F, int HW, int Cpad) {
+  const long long total = (long long)dup * F * HW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int px = (int)(t % HW);
+  const int f = (int)((t / HW) % F);
+  const uint2 v = *reinterpret_cast<const uint2*>(lat + ((long long)idx[f] * HW + px) * 4);
+  uint4* o = reinterpret_cast<uint4*>(out + t * Cpad);
+  o[0] = make_uint4(v.x, v.y, 0u, 0u);
+  for (int u = 1; u < Cpad / 8; ++u) o[u] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// acc[b, idx[f], px, :] += pred[(b, f), px, 0..4)   (fp32 accumulation of overlapping windows)
+__global__ void scatter_accumulate_kernel(const __half* __restrict__ pred, int ld, const int* __restrict__ idx,
+                                          float* __restrict__ acc, int B, int F, int L, int HW) {
+  const long long total = (long long)B * F * HW;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int px = (int)(t % HW);
+  const int f = (int)((t / HW) % F);
+  const int b = (int)(t / ((long long)HW * F));
+  const __half* s = pred + t * ld;
+  float4* d = reinterpret_cast<float4*>(acc + (((long long)b * L + idx[f]) * HW + px) * 4);
+  float4 a = *d;
+  a.x += __half2float(s[0]); a.y += __half2float(s[1]); a.z += __half2float(s[2]); a.w += __half2float(s[3]);
+  *d = a;
+}
+
+// noise = acc / count ; CFG: u + g (c - u) ; DDIM v-prediction step (eta = 0) ; latents updated in place; acc zeroed.
+__global__ void cfg_ddim_step_kernel(float* __restrict__ acc, const float* __restrict__ inv_count, int cfg, float guidance,
+                                     float sqrt_at, float sqrt_bt, float sqrt_ap, float sqrt_bp,
+                                     __half* __restrict__ lat, int L, int HW) {
+  const long long total = (long long)L * HW * 4;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int f = (int)(t / ((long long)HW * 4));
+  const float ic = inv_count[f];
+  float v;
+  if (cfg) {
+    const float u = acc[t] * ic;
+    const float c = acc[total + t] * ic;
+    v = u + guidance * (c - u);
+    acc[total + t] = 0.f;
+  } else {
+    v = acc[t] * ic;
+  }
+  acc[t] = 0.f;
+  const float x = __half2float(lat[t]);
+  const float x0 = sqrt_at * x - sqrt_bt * v;
+  const float eps = sqrt_at * v + sqrt_bt * x;
+  lat[t] = __float2half_rn(sqrt_ap * x0 + sqrt_bp * eps);
+}
+
+static inline unsigned grid_for(long long n, int threads, int cap = 148 * 16) {
+  long long g = (n + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace ap
+
+using namespace ap;
+
+extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* out, long long ldo, int B, int F, int N,
+                                         int C, int heads, float scale, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AP_REQUIRE(qkv && out, "temporal_attention: null pointer");
+  AP_REQUIRE(F >= 1 && F <= 32, "temporal_attention: window length %d not in [1,32]", F);
+  AP_REQUIRE(heads >= 1 && heads <= 8 && C % heads == 0, "temporal_attention: heads=%d unsupported", heads);
+  const int d = C / heads;
+  AP_REQUIRE(d % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "temporal_attention: head_dim/ld must be multiples of 8");
+  int CH = 8;
+  for (int c : {40, 32, 16, 8})
+    if (d % c == 0) { CH = c; break; }
+  const int FP = F <= 4 ? 4 : (F <= 8 ? 8 : (F <= 16 ? 16 : 32));
+  const int PW = 32 / FP;
+  const long long groups = (long long)B * ((N + PW - 1) / PW);
+  const size_t smem = (size_t)8 * PW * FP * CH * sizeof(__half);
+#define AP_T(FP_)                                                                                              \
+  temporal_attn_kernel<FP_><<<(unsigned)groups, 256, smem, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, B, F, \
+                                                                     N, C, heads, CH, scale)
+  if (FP == 4) AP_T(4);
+  else if (FP == 8) AP_T(8);
+  else if (FP == 16) AP_T(16);
+  else AP_T(32);
+#undef AP_T
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_add_f16(const void* a, const void* b, void* out, long long n, void* stream) {
+  AP_REQUIRE(a && b && out && n % 8 == 0, "add: n must be a multiple of 8");
+  add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_silu_f16(const void* x, void* out, long long n, void* stream) {
+  AP_REQUIRE(x && out, "silu: null pointer");
+  silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, n);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_upsample2x_nhwc_f16(const void* x, void* out, int Nf, int H, int W, int C, void* stream) {
+  AP_REQUIRE(x && out && C % 8 == 0, "upsample2x: C must be a multiple of 8");
+  const long long total = (long long)Nf * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, Nf, H, W, C / 8);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_ncfhw_to_nhwc_f16(const void* x, void* out, int B, int C, int F, int HW, int Cpad, void* stream) {
+  AP_REQUIRE(x && out && Cpad >= C, "ncfhw_to_nhwc: bad arguments");
+  const long long total = (long long)B * F * HW * Cpad;
+  ncfhw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, B, C, F, HW, Cpad);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_nhwc_to_ncfhw_f16(const void* x, void* out, int B, int C, int F, int HW, int ld, void* stream) {
+  AP_REQUIRE(x && out && ld >= C, "nhwc_to_ncfhw: bad arguments");
+  const long long total = (long long)B * C * F * HW;
+  nhwc_to_ncfhw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, B, C, F, HW, ld);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_gather_window_f16(const void* latents, const int* frame_idx, void* out, int dup, int F, int HW,
+                                    int Cpad, void* stream) {
+  AP_REQUIRE(latents && frame_idx && out && Cpad % 8 == 0 && Cpad >= 8, "gather_window: bad arguments");
+  const long long total = (long long)dup * F * HW;
+  gather_window_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)latents, frame_idx, (__half*)out, dup, F, HW, Cpad);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_scatter_accumulate_f16(const void* pred, int ld, const int* frame_idx, float* acc, int B, int F,
+                                         int L, int HW, void* stream) {
+  AP_REQUIRE(pred && frame_idx && acc, "scatter_accumulate: null pointer");
+  const long long total = (long long)B * F * HW;
+  scatter_accumulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)pred, ld, frame_idx, acc, B, F, L, HW);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg, float guidance, float alpha_t,
+                                    float alpha_prev, void* latents, int L, int HW, void* stream) {
+  AP_REQUIRE(acc && inv_count && latents, "cfg_ddim_step: null pointer");
+  const long long total = (long long)L * HW * 4;
+  cfg_ddim_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      acc, inv_count, cfg, guidance, sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev),
+      (__half*)latents, L, HW);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}

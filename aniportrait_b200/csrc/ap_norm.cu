@@ -1,0 +1,258 @@
+// GroupNorm (two-phase, channels-last) and LayerNorm kernels. These are HBM-bound streaming kernels: 16-byte
+// vectorised, coalesced accesses, fp32 statistics.
+//
+// Replaces InflatedGroupNorm / nn.GroupNorm (+SiLU) (reference src/models/resnet.py:21-29,221-222,232-238;
+// src/models/transformer_3d.py:58-60,124; src/models/motion_module.py:119-121,156; src/models/unet_3d.py:238-249,573-574)
+// and nn.LayerNorm (+ temporal positional-encoding add) (src/models/attention.py:331-362;
+// src/models/motion_module.py:228-241,262-277,365-366).
+#include "ap_host.h"
+
+namespace ap {
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[frame][group] = {sum, sumsq} over (HW x channels-per-group).
+// grid (row_chunks, Nf); block = (C/8) * k threads; thread owns 8 consecutive channels, strides over rows.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int c_off, int cpg, int rows_per_block,
+                                float* __restrict__ stats, int G) {
+  const int vecs = C >> 3;
+  const int k = blockDim.x / vecs;
+  const int cv = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int frame = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, HW);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (rl < k) {
+    const __half* base = x + ((long long)frame * HW) * C + cv * 8;
+    for (int r = r0 + rl; r < r1; r += k) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * C));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+  }
+  extern __shared__ float sg[];  // [G][2]
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sg[i] = 0.f;
+  __syncthreads();
+  if (rl < k) {
+    // merge the 8 channels into (at most 2..8) groups before touching shared memory
+    int g_prev = (c_off + cv * 8) / cpg;
+    float as = 0.f, aq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c_off + cv * 8 + j) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&sg[2 * g_prev], as);
+        atomicAdd(&sg[2 * g_prev + 1], aq);
+        as = aq = 0.f;
+        g_prev = g;
+      }
+      as += s[j];
+      aq += q[j];
+    }
+    atomicAdd(&sg[2 * g_prev], as);
+    atomicAdd(&sg[2 * g_prev + 1], aq);
+  }
+  __syncthreads();
+  const int g_lo = c_off / cpg, g_hi = (c_off + C - 1) / cpg;
+  for (int g = g_lo + threadIdx.x; g <= g_hi; g += blockDim.x) {
+    atomicAdd(&stats[((long long)frame * G + g) * 2], sg[2 * g]);
+    atomicAdd(&stats[((long long)frame * G + g) * 2 + 1], sg[2 * g + 1]);
+  }
+}
+
+// Apply: y = (x - mean) * rstd * gamma + beta  (optionally SiLU), written at channel offset c_off of an
+// [rows, C_total] output (this is also how the skip-concat gets materialised, in normalised form, for free).
+template <bool SILU>
+__global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int c_off, int C_total, int cpg,
+                                int rows_per_block, const float* __restrict__ stats, int G, float inv_count,
+                                float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __half* __restrict__ y) {
+  const int vecs = C >> 3;
+  const int k = blockDim.x / vecs;
+  const int cv = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  if (rl >= k) return;
+  const int frame = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, HW);
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c_off + cv * 8 + j;
+    const int g = c / cpg;
+    const float sum = stats[((long long)frame * G + g) * 2];
+    const float sq = stats[((long long)frame * G + g) * 2 + 1];
+    const float mean = sum * inv_count;
+    const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    a[j] = rstd * gamma[c];
+    b[j] = beta[c] - mean * a[j];
+  }
+  const __half* src = x + ((long long)frame * HW) * C + cv * 8;
+  __half* dst = y + ((long long)frame * HW) * C_total + c_off + cv * 8;
+  for (int r = r0 + rl; r < r1; r += k) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * C));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      float v0 = f.x * a[2 * j] + b[2 * j];
+      float v1 = f.y * a[2 * j + 1] + b[2 * j + 1];
+      if (SILU) {
+        v0 = v0 / (1.f + __expf(-v0));
+        v1 = v1 / (1.f + __expf(-v1));
+      }
+      o2[j] = __floats2half2_rn(v0, v1);
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)r * C_total) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim, one warp per row, values kept in registers (exact two-pass statistics).
+// Optional additive table pe[(row / rows_per_pe) % pe_period][C] (the temporal positional encoding, which the
+// reference adds to the LayerNorm output before the q/k/v projections).
+// ---------------------------------------------------------------------------------------------------------
+template <int MAXV>  // MAXV = max half2 per lane  (C <= 64 * MAXV)
+__global__ void layernorm_kernel(const __half* __restrict__ x, long long rows, int C, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ pe, int rows_per_pe, int pe_period,
+                                 __half* __restrict__ y) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 1;  // half2 per row
+  const __half2* src = reinterpret_cast<const __half2*>(x + row * C);
+  float2 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      v[i] = __half22float2(src[idx]);
+      sum += v[i].x + v[i].y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean;
+      sq += dx * dx + dy * dy;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  const float* pe_row = pe ? pe + (long long)((row / rows_per_pe) % pe_period) * C : nullptr;
+  __half2* dst = reinterpret_cast<__half2*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * idx);
+      const float2 b = *reinterpret_cast<const float2*>(beta + 2 * idx);
+      float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+      float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      if (pe_row) {
+        const float2 p = *reinterpret_cast<const float2*>(pe_row + 2 * idx);
+        o0 += p.x;
+        o1 += p.y;
+      }
+      dst[idx] = __floats2half2_rn(o0, o1);
+    }
+  }
+}
+
+static void gn_launch_geometry(int HW, int C, int Nf, int* threads, int* rows_per_block, int* chunks) {
+  const int vecs = C / 8;
+  int k = 256 / vecs;
+  if (k < 1) k = 1;
+  *threads = vecs * k;
+  // aim for >= ~4 waves of 148 SMs when the tensor is large, but at least 8 rows per row-lane
+  int rpb = 8 * k;
+  while ((long long)((HW + rpb - 1) / rpb) * Nf > 148 * 16 && rpb < HW) rpb *= 2;
+  *rows_per_block = rpb;
+  *chunks = (HW + rpb - 1) / rpb;
+}
+
+}  // namespace ap
+
+using namespace ap;
+
+// stats: fp32 [Nf, G, 2] workspace (zeroed here). x2/C2 optional second source (channel concat).
+extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int HW, int groups,
+                                     float eps, const float* gamma, const float* beta, int silu, float* stats,
+                                     void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int C = C1 + (x2 ? C2 : 0);
+  AP_REQUIRE(x && out && stats && gamma && beta, "groupnorm: null pointer");
+  AP_REQUIRE(C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
+  AP_REQUIRE(C1 % 8 == 0 && (!x2 || C2 % 8 == 0), "groupnorm: channel counts must be multiples of 8");
+  AP_REQUIRE(C1 / 8 <= 1024 && (!x2 || C2 / 8 <= 1024), "groupnorm: too many channels");
+  const int cpg = C / groups;
+  AP_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * Nf, stream));
+  const void* srcs[2] = {x, x2};
+  const int cs[2] = {C1, C2};
+  const int offs[2] = {0, C1};
+  for (int s = 0; s < (x2 ? 2 : 1); ++s) {
+    int threads, rpb, chunks;
+    gn_launch_geometry(HW, cs[s], Nf, &threads, &rpb, &chunks);
+    gn_stats_kernel<<<dim3(chunks, Nf), threads, sizeof(float) * 2 * groups, stream>>>(
+        (const __half*)srcs[s], HW, cs[s], offs[s], cpg, rpb, stats, groups);
+  }
+  AP_CHECK_CUDA(cudaGetLastError());
+  const float inv_count = 1.0f / ((float)HW * (float)cpg);
+  for (int s = 0; s < (x2 ? 2 : 1); ++s) {
+    int threads, rpb, chunks;
+    gn_launch_geometry(HW, cs[s], Nf, &threads, &rpb, &chunks);
+    if (silu)
+      gn_apply_kernel<true><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
+                                                                      cpg, rpb, stats, groups, inv_count, eps, gamma,
+                                                                      beta, (__half*)out);
+    else
+      gn_apply_kernel<false><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
+                                                                       cpg, rpb, stats, groups, inv_count, eps, gamma,
+                                                                       beta, (__half*)out);
+  }
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_layernorm_f16(const void* x, long long rows, int C, float eps, const float* gamma,
+                                const float* beta, const float* pe, int rows_per_pe, int pe_period, void* out,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AP_REQUIRE(x && out && gamma && beta, "layernorm: null pointer");
+  AP_REQUIRE(C % 2 == 0 && C <= 64 * 32, "layernorm: C=%d unsupported (even, <= 2048)", C);
+  AP_REQUIRE(pe == nullptr || (rows_per_pe > 0 && pe_period > 0), "layernorm: bad pe geometry");
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const int maxv = (C / 2 + 31) / 32;
+#define AP_LN(MV)                                                                                              \
+  layernorm_kernel<MV><<<grid, wpb * 32, 0, stream>>>((const __half*)x, rows, C, eps, gamma, beta, pe,          \
+                                                      rows_per_pe > 0 ? rows_per_pe : 1, pe_period > 0 ? pe_period : 1, \
+                                                      (__half*)out)
+  if (maxv <= 5) AP_LN(5);
+  else if (maxv <= 10) AP_LN(10);
+  else if (maxv <= 20) AP_LN(20);
+  else AP_LN(32);
+#undef AP_LN
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}

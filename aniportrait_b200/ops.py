@@ -119,3 +119,218 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, cout: int, bias: torch.Tens
     check(rc, "ap_conv3x3_nhwc_f16")
     _count()
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# normalisation
+# --------------------------------------------------------------------------------------------------------------
+_stats_ws = {}
+
+
+def _stats_workspace(device, n):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _stats_ws.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 4096), dtype=torch.float32, device=device)
+        _stats_ws[key] = buf
+    return buf
+
+
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+               x2: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x: [Nf, HW, C1] (or [Nf,H,W,C1]) fp16 channels-last; optional x2 concatenated along C. gamma/beta fp32 [C]."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    nf, c1 = x.shape[0], x.shape[-1]
+    hw = x.numel() // (nf * c1)
+    c2 = 0
+    if x2 is not None:
+        assert x2.is_contiguous() and x2.shape[0] == nf
+        c2 = x2.shape[-1]
+    c = c1 + c2
+    assert gamma.dtype == torch.float32 and gamma.numel() == c and beta.numel() == c
+    if out is None:
+        out = torch.empty(*x.shape[:-1], c, dtype=torch.float16, device=x.device)
+    stats = _stats_workspace(x.device, 2 * groups * nf)
+    rc = lib().ap_groupnorm_nhwc_f16(ptr(x), I(c1), ptr(x2), I(c2), I(nf), I(hw), I(groups), _lib.c_float(eps),
+                                     fptr(gamma), fptr(beta), I(1 if silu else 0), fptr(stats), ptr(out),
+                                     stream_ptr())
+    check(rc, "ap_groupnorm_nhwc_f16")
+    _count(5 if x2 is not None else 3)
+    return out
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+               pe: torch.Tensor | None = None, rows_per_pe: int = 0, pe_period: int = 0,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """x: [rows, C] fp16; pe: optional fp32 [pe_period, C] added after the affine (row r uses pe[(r//rows_per_pe)%period])."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 2
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    if pe is not None:
+        assert pe.dtype == torch.float32 and pe.is_contiguous() and pe.shape[-1] == c and pe.shape[0] >= pe_period
+    rc = lib().ap_layernorm_f16(ptr(x), LL(rows), I(c), _lib.c_float(eps), fptr(gamma), fptr(beta), fptr(pe),
+                                I(rows_per_pe), I(pe_period), ptr(out), stream_ptr())
+    check(rc, "ap_layernorm_f16")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------------------
+def head_pad(d: int) -> int:
+    """Head dim padded to a whole number of 64-column swizzle atoms (40->64, 80->128, 88->128, 160->192)."""
+    p = (d + 63) // 64 * 64
+    if p > 192:
+        raise _lib.ApError(f"head_dim {d} > 192 is not supported by the fused attention kernel")
+    return p
+
+
+def pad_head_rows(w: torch.Tensor, heads: int, dpad: int) -> torch.Tensor:
+    """Projection weight [heads*d, K] -> [heads*dpad, K] with zero rows after each head's d rows."""
+    hd, k = w.shape
+    d = hd // heads
+    out = torch.zeros(heads, dpad, k, dtype=w.dtype, device=w.device)
+    out[:, :d] = w.view(heads, d, k)
+    return out.reshape(heads * dpad, k).contiguous()
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_frames: int, tokens: int, heads: int,
+              head_dim: int, dpad: int, bank_k: torch.Tensor | None = None, bank_v: torch.Tensor | None = None,
+              bank_tokens: int = 0, n_banks: int = 0, first_bank_frame: int = 0, frames_per_bank: int = 1,
+              scale: float | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """q/k/v: column-slices [n_frames*tokens, heads*dpad] of one fp16 buffer (same row stride); returns
+    [n_frames*tokens, heads*head_dim]."""
+    _ensure(q)
+    rows = n_frames * tokens
+    for t in (q, k, v):
+        assert t.dtype == torch.float16 and t.shape == (rows, heads * dpad) and t.stride(1) == 1
+        assert t.stride(0) == q.stride(0)
+    if out is None:
+        out = torch.empty(rows, heads * head_dim, dtype=torch.float16, device=q.device)
+    ld_bank = 0
+    if bank_k is not None:
+        assert bank_k.shape == (n_banks * bank_tokens, heads * dpad) and bank_k.stride(1) == 1
+        assert bank_v.shape == bank_k.shape and bank_v.stride(0) == bank_k.stride(0)
+        ld_bank = bank_k.stride(0)
+    if scale is None:
+        scale = head_dim ** -0.5
+    rc = lib().ap_attention_f16(ptr(q), ptr(k), ptr(v), LL(q.stride(0)), ptr(bank_k), ptr(bank_v), LL(ld_bank),
+                                I(bank_tokens), I(n_banks), I(n_frames), I(tokens), I(heads), I(head_dim), I(dpad),
+                                I(first_bank_frame), I(frames_per_bank), _lib.c_float(scale), ptr(out),
+                                LL(out.stride(0)), stream_ptr())
+    check(rc, "ap_attention_f16")
+    _count()
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, B: int, F: int, N: int, C: int, heads: int,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    _ensure(qkv)
+    assert qkv.dtype == torch.float16 and qkv.shape == (B * F * N, 3 * C) and qkv.stride(1) == 1
+    if out is None:
+        out = torch.empty(B * F * N, C, dtype=torch.float16, device=qkv.device)
+    scale = (C // heads) ** -0.5
+    rc = lib().ap_temporal_attention_f16(ptr(qkv), LL(qkv.stride(0)), ptr(out), LL(out.stride(0)), I(B), I(F), I(N),
+                                         I(C), I(heads), _lib.c_float(scale), stream_ptr())
+    check(rc, "ap_temporal_attention_f16")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# elementwise / layout
+# --------------------------------------------------------------------------------------------------------------
+def add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _ensure(a)
+    assert a.dtype == torch.float16 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().ap_add_f16(ptr(a), ptr(b), ptr(out), LL(a.numel()), stream_ptr()), "ap_add_f16")
+    _count()
+    return out
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    out = torch.empty_like(x)
+    check(lib().ap_silu_f16(ptr(x), ptr(out), LL(x.numel()), stream_ptr()), "ap_silu_f16")
+    _count()
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _ensure(x)
+    nf, h, w, c = x.shape
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    out = torch.empty(nf, 2 * h, 2 * w, c, dtype=torch.float16, device=x.device)
+    check(lib().ap_upsample2x_nhwc_f16(ptr(x), ptr(out), I(nf), I(h), I(w), I(c), stream_ptr()), "ap_upsample2x")
+    _count()
+    return out
+
+
+def ncfhw_to_nhwc(x: torch.Tensor, cpad: int) -> torch.Tensor:
+    """[B, C, F, H, W] -> [(B F), H, W, cpad] (zero padded channels)."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 5
+    b, c, f, h, w = x.shape
+    out = torch.empty(b * f, h, w, cpad, dtype=torch.float16, device=x.device)
+    check(lib().ap_ncfhw_to_nhwc_f16(ptr(x), ptr(out), I(b), I(c), I(f), I(h * w), I(cpad), stream_ptr()),
+          "ap_ncfhw_to_nhwc_f16")
+    _count()
+    return out
+
+
+def nhwc_to_ncfhw(x: torch.Tensor, B: int, C: int, F: int) -> torch.Tensor:
+    """[(B F), H, W, ld>=C] -> [B, C, F, H, W]."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 4 and x.shape[0] == B * F
+    _, h, w, ld = x.shape
+    out = torch.empty(B, C, F, h, w, dtype=torch.float16, device=x.device)
+    check(lib().ap_nhwc_to_ncfhw_f16(ptr(x), ptr(out), I(B), I(C), I(F), I(h * w), I(ld), stream_ptr()),
+          "ap_nhwc_to_ncfhw_f16")
+    _count()
+    return out
+
+
+def gather_window(latents: torch.Tensor, frame_idx: torch.Tensor, dup: int, cpad: int = 64) -> torch.Tensor:
+    """latents [L, H, W, 4] fp16 -> UNet input [(dup F), H, W, cpad]."""
+    _ensure(latents)
+    L, h, w, c = latents.shape
+    assert c == 4 and latents.dtype == torch.float16 and latents.is_contiguous() and frame_idx.dtype == torch.int32
+    F = frame_idx.numel()
+    out = torch.empty(dup * F, h, w, cpad, dtype=torch.float16, device=latents.device)
+    check(lib().ap_gather_window_f16(ptr(latents), _lib.ctypes.cast(_lib.c_void_p(frame_idx.data_ptr()),
+                                                                     _lib.POINTER(_lib.c_int)),
+                                     ptr(out), I(dup), I(F), I(h * w), I(cpad), stream_ptr()), "ap_gather_window_f16")
+    _count()
+    return out
+
+
+def scatter_accumulate(pred: torch.Tensor, frame_idx: torch.Tensor, acc: torch.Tensor):
+    """pred [(B F), H, W, ld] fp16 (first 4 channels) accumulated into acc fp32 [B, L, H, W, 4] at frame_idx."""
+    _ensure(pred)
+    B, L, h, w, _ = acc.shape
+    F = frame_idx.numel()
+    assert pred.shape[0] == B * F and acc.dtype == torch.float32 and acc.is_contiguous() and pred.is_contiguous()
+    check(lib().ap_scatter_accumulate_f16(ptr(pred), I(pred.shape[-1]),
+                                          _lib.ctypes.cast(_lib.c_void_p(frame_idx.data_ptr()), _lib.POINTER(_lib.c_int)),
+                                          fptr(acc), I(B), I(F), I(L), I(h * w), stream_ptr()),
+          "ap_scatter_accumulate_f16")
+    _count()
+
+
+def cfg_ddim_step(acc: torch.Tensor, inv_count: torch.Tensor, guidance: float, alpha_t: float, alpha_prev: float,
+                  latents: torch.Tensor):
+    """In place: latents <- DDIM v-prediction step of the CFG-combined, overlap-averaged prediction; acc zeroed."""
+    _ensure(latents)
+    B, L, h, w, _ = acc.shape
+    assert latents.shape == (L, h, w, 4) and latents.dtype == torch.float16 and inv_count.dtype == torch.float32
+    check(lib().ap_cfg_ddim_step_f16(fptr(acc), fptr(inv_count), I(1 if B == 2 else 0), _lib.c_float(guidance),
+                                     _lib.c_float(alpha_t), _lib.c_float(alpha_prev), ptr(latents), I(L), I(h * w),
+                                     stream_ptr()), "ap_cfg_ddim_step_f16")
+    _count()

@@ -61,6 +61,64 @@ int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, i
                         const void* w, int Cout, const float* bias, long long bias_group_rows,
                         const void* residual, void* out, long long ldo, int n_valid, int block_n, void* stream);
 
+/*
+ * GroupNorm over channels-last activations, optional fused SiLU, optional second source concatenated along channels
+ * (the normalised concat of [hidden, skip] is written once, replacing torch.cat + GroupNorm + SiLU).
+ * Replaces InflatedGroupNorm / nn.GroupNorm (reference src/models/resnet.py:21-29,221-222,232-238;
+ * src/models/transformer_3d.py:124; src/models/motion_module.py:156; src/models/unet_3d.py:573-574).
+ * x: [Nf, HW, C1], x2: [Nf, HW, C2] or NULL, out: [Nf, HW, C1+C2]; statistics per (frame, group) in fp32.
+ * stats: caller-provided fp32 workspace of 2*groups*Nf floats.
+ */
+int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int HW, int groups, float eps,
+                          const float* gamma, const float* beta, int silu, float* stats, void* out, void* stream);
+
+/*
+ * LayerNorm over the last dim (+ optional additive table pe[(row / rows_per_pe) % pe_period][C], the motion module's
+ * sinusoidal frame encoding which the reference adds to the LayerNorm output, src/models/motion_module.py:365-366).
+ * Replaces nn.LayerNorm (reference src/models/attention.py:331-362; src/models/motion_module.py:228-241).
+ */
+int ap_layernorm_f16(const void* x, long long rows, int C, float eps, const float* gamma, const float* beta,
+                     const float* pe, int rows_per_pe, int pe_period, void* out, void* stream);
+
+/*
+ * Fused spatial self / reference attention (flash-style, tcgen05). q/k/v: [n_frames*tokens, ld_qkv] fp16 with head h
+ * at columns [h*dpad, h*dpad + head_dim) (zero padded to dpad in {64,128,192}); frames >= first_bank_frame also attend
+ * to bank (frame - first_bank_frame) / frames_per_bank of bank_k/bank_v: [n_banks*bank_tokens, ld_bank] (NULL = none).
+ * out: [n_frames*tokens, ldo], head h at columns [h*head_dim, (h+1)*head_dim).
+ * Replaces F.scaled_dot_product_attention under ReferenceAttentionControl's read-mode forward, including the CFG
+ * redo for the unconditional half (reference src/models/mutual_self_attention.py:147-186; src/models/attention.py:323-330).
+ */
+int ap_attention_f16(const void* q, const void* k, const void* v, long long ld_qkv, const void* bank_k,
+                     const void* bank_v, long long ld_bank, int bank_tokens, int n_banks, int n_frames, int tokens,
+                     int heads, int head_dim, int dpad, int first_bank_frame, int frames_per_bank, float scale,
+                     void* out, long long ldo, void* stream);
+
+/*
+ * Temporal attention core of the motion module: softmax over the F frames of each (batch, position, head).
+ * qkv: [B*F*N, ld] = [q | k | v] (C columns each, token row (b*F+f)*N+p); out: [B*F*N, ldo].
+ * Replaces VersatileAttention's rearrange + SDPA + rearrange (reference src/models/motion_module.py:351-388).
+ */
+int ap_temporal_attention_f16(const void* qkv, long long ld, void* out, long long ldo, int B, int F, int N, int C,
+                              int heads, float scale, void* stream);
+
+/* Elementwise / layout helpers (fp16, n % 8 == 0 where vectorised). */
+int ap_add_f16(const void* a, const void* b, void* out, long long n, void* stream);          /* unet_3d.py:485-486,508-510 */
+int ap_silu_f16(const void* x, void* out, long long n, void* stream);                        /* resnet.py:226-230 */
+int ap_upsample2x_nhwc_f16(const void* x, void* out, int Nf, int H, int W, int C, void* stream); /* resnet.py:71-78 */
+int ap_ncfhw_to_nhwc_f16(const void* x, void* out, int B, int C, int F, int HW, int Cpad, void* stream);
+int ap_nhwc_to_ncfhw_f16(const void* x, void* out, int B, int C, int F, int HW, int ld, void* stream);
+
+/*
+ * Denoising-loop elementwise ops (reference src/pipelines/pipeline_pose2vid_long.py:521-559 and diffusers
+ * DDIMScheduler.step, v-prediction, eta = 0). latents: fp16 [L, HW, 4] channels-last; acc: fp32 [B, L, HW, 4].
+ */
+int ap_gather_window_f16(const void* latents, const int* frame_idx, void* out, int dup, int F, int HW, int Cpad,
+                         void* stream);
+int ap_scatter_accumulate_f16(const void* pred, int ld, const int* frame_idx, float* acc, int B, int F, int L, int HW,
+                              void* stream);
+int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg, float guidance, float alpha_t, float alpha_prev,
+                         void* latents, int L, int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
