@@ -45,6 +45,7 @@ struct GemmParams {
   __half* out;             // [M, ldo]
   int ldo;
   int n_valid;             // columns >= n_valid are not stored
+  int out_f32;             // store fp32 instead of fp16 (small bias-table GEMMs)
 };
 
 template <int BN>
@@ -275,7 +276,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               }
             }
             __half* dst = p.out + m * p.ldo + ncol;
-            if (vec_ok) {
+            if (p.out_f32) {
+              float* dstf = reinterpret_cast<float*>(p.out) + m * p.ldo + ncol;
+              for (int j = 0; j < 32; ++j)
+                if (ncol + j < p.n_valid) dstf[j] = v[j];
+            } else if (vec_ok) {
               uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -397,6 +402,8 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
   p.ldo = (int)ldo;
   const int nout = epi == EPI_GEGLU ? N / 2 : N;
   p.n_valid = n_valid > 0 ? n_valid : nout;
+  p.out_f32 = (flags & AP_GEMM_OUT_F32) ? 1 : 0;
+  AP_REQUIRE(!(p.out_f32 && epi == EPI_GEGLU), "gemm: fp32 output is not available with GEGLU");
 
   CUtensorMap tmA1, tmA2, tmB;
   {

@@ -139,6 +139,36 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
   }
 }
 
+__global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
+                                 long long nvec, long long nbvec) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; idx < nvec; idx += stride) {
+    const uint4 x = __ldg(a + idx), y = __ldg(b + idx % nbvec);
+    uint4 r;
+    const __half2* x2 = reinterpret_cast<const __half2*>(&x);
+    const __half2* y2 = reinterpret_cast<const __half2*>(&y);
+    __half2* r2 = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fx = __half22float2(x2[t]), fy = __half22float2(y2[t]);
+      r2[t] = __floats2half2_rn(fx.x + fy.x, fx.y + fy.y);
+    }
+    o[idx] = r;
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx % half;
+  const float freq = expf(-9.210340371976184f * (float)i / (float)half);  // ln(10000)
+  const float arg = t[b] * freq;
+  out[b * dim + i] = __float2half_rn(cosf(arg));
+  out[b * dim + half + i] = __float2half_rn(sinf(arg));
+}
+
 __global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) {
@@ -298,6 +328,22 @@ extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* ou
 extern "C" int ap_add_f16(const void* a, const void* b, void* out, long long n, void* stream) {
   AP_REQUIRE(a && b && out && n % 8 == 0, "add: n must be a multiple of 8");
   add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_add_bcast_f16(const void* a, const void* b, void* out, long long n, long long nb, void* stream) {
+  AP_REQUIRE(a && b && out && n % 8 == 0 && nb % 8 == 0 && nb > 0 && n % nb == 0, "add_bcast: bad sizes");
+  add_bcast_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+                                                                         n / 8, nb / 8);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_timestep_embedding_f16(const float* t, int B, int dim, void* out, void* stream) {
+  AP_REQUIRE(t && out && dim % 2 == 0, "timestep_embedding: bad arguments");
+  const int n = B * dim / 2;
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, B, dim, (__half*)out);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }

@@ -1,0 +1,406 @@
+"""Building blocks shared by the denoising UNet3D and the ReferenceNet UNet2D mirrors.
+
+Every class keeps the reference's attribute tree so that `state_dict()` keys (and the published checkpoints:
+denoising_unet.pth, motion_module.pth, reference_unet.pth) are interchangeable with the reference's
+src/models/{resnet,transformer_3d,attention,motion_module,unet_3d_blocks,unet_2d_blocks}.py. Their forward passes,
+however, are sequences of the sm_100a kernels in aniportrait_b200/csrc operating on channels-last fp16 activations
+`[frames, H, W, C]` (== token matrices `[frames*H*W, C]`, so conv <-> attention hand-offs are zero-copy). There is no
+torch-op fallback: running a block on a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .. import ops
+from .modeling import PackedCache, f16, f32
+
+
+class RunCtx:
+    """Per-forward state threaded through the blocks."""
+
+    def __init__(self, batch: int, frames: int, temb_act: torch.Tensor | None, ehs: torch.Tensor | None,
+                 ehs_key=None):
+        self.B = batch              # CFG branches x videos
+        self.F = frames             # frames per batch element (1 for the 2-D ReferenceNet)
+        self.temb_act = temb_act    # SiLU(time embedding) [B, 1280] fp16
+        self.ehs = ehs              # encoder hidden states [B, S, 768] fp16
+        self.ehs_key = ehs_key
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameter holders that mirror diffusers' module tree
+# ------------------------------------------------------------------------------------------------------------
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """diffusers FeedForward(activation_fn='geglu'): net.0.proj, net.2 (reference src/models/attention.py:361)."""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+        self._pk = PackedCache()
+
+    def packed(self):
+        def build():
+            w1, b1 = ops.interleave_geglu(f16(self.net[0].proj.weight), f32(self.net[0].proj.bias))
+            return dict(w1=w1, b1=b1, w2=f16(self.net[2].weight), b2=f32(self.net[2].bias))
+        return self._pk.get(self, build)
+
+    def run(self, x_norm: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+        pk = self.packed()
+        h = ops.gemm(x_norm, pk["w1"], bias=pk["b1"], geglu=True)
+        return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=residual)
+
+
+class Attention(nn.Module):
+    """diffusers Attention parameters: to_q, to_k, to_v (no bias), to_out.0 (bias)."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64):
+        super().__init__()
+        inner = heads * dim_head
+        kv_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.heads = heads
+        self.dim_head = dim_head
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(kv_dim, inner, bias=False)
+        self.to_v = nn.Linear(kv_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# ResnetBlock (3-D inflated == per-frame 2-D)
+# ------------------------------------------------------------------------------------------------------------
+class ResnetBlock(nn.Module):
+    """ResnetBlock3D / diffusers ResnetBlock2D (reference src/models/resnet.py:124-248):
+    GN+SiLU -> conv3x3 (+ time-embedding bias) -> GN+SiLU -> conv3x3 (+ residual | 1x1 shortcut)."""
+
+    def __init__(self, in_channels, out_channels, temb_channels=1280, groups=32, eps=1e-5):
+        super().__init__()
+        self.in_channels, self.out_channels, self.groups, self.eps = in_channels, out_channels, groups, eps
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+        self._pk = PackedCache()
+
+    def packed(self):
+        def build():
+            d = dict(g1=f32(self.norm1.weight), b1=f32(self.norm1.bias), g2=f32(self.norm2.weight),
+                     b2=f32(self.norm2.bias), w1=ops.pack_conv3x3_weight(self.conv1.weight.detach()),
+                     w2=ops.pack_conv3x3_weight(self.conv2.weight.detach()), cb2=f32(self.conv2.bias))
+            if self.time_emb_proj is not None:
+                d["wt"] = f16(self.time_emb_proj.weight)
+                d["bt"] = f32(self.time_emb_proj.bias) + f32(self.conv1.bias)   # conv1 bias folded into the temb bias
+            else:
+                d["cb1"] = f32(self.conv1.bias)
+            if self.conv_shortcut is not None:
+                d["ws"] = f16(self.conv_shortcut.weight.reshape(self.out_channels, self.in_channels))
+                d["bs"] = f32(self.conv_shortcut.bias)
+            return d
+        return self._pk.get(self, build)
+
+    def run(self, x: torch.Tensor, ctx: RunCtx, skip: torch.Tensor | None = None) -> torch.Tensor:
+        """x: [Nf,H,W,C1]; skip: optional [Nf,H,W,C2] (the reference's torch.cat([x, skip], dim=1))."""
+        pk = self.packed()
+        nf, h, w, _ = x.shape
+        cout = self.out_channels
+        hn = ops.group_norm(x, pk["g1"], pk["b1"], self.groups, self.eps, True, x2=skip)
+        if self.time_emb_proj is not None:
+            bias1 = ops.gemm(ctx.temb_act, pk["wt"], bias=pk["bt"], out_f32=True)            # [B, cout] fp32
+            hc = ops.conv3x3(hn, pk["w1"], cout, bias=bias1, bias_group_rows=ctx.F * h * w)
+        else:
+            hc = ops.conv3x3(hn, pk["w1"], cout, bias=pk["cb1"])
+        hn2 = ops.group_norm(hc, pk["g2"], pk["b2"], self.groups, self.eps, True)
+        if self.conv_shortcut is not None:
+            c1 = x.shape[-1]
+            a = x.view(-1, c1)
+            a2 = skip.view(-1, skip.shape[-1]) if skip is not None else None
+            res = ops.gemm(a, pk["ws"], bias=pk["bs"], a2=a2).view(nf, h, w, cout)
+        else:
+            assert skip is None
+            res = x
+        return ops.conv3x3(hn2, pk["w2"], cout, bias=pk["cb2"], residual=res)
+
+
+class Downsample(nn.Module):
+    """Downsample3D / Downsample2D(name='op'): conv3x3 stride 2 padding 1 (reference src/models/resnet.py:94-121)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+        self._pk = PackedCache()
+
+    def run(self, x):
+        pk = self._pk.get(self, lambda: dict(w=ops.pack_conv3x3_weight(self.conv.weight.detach()), b=f32(self.conv.bias)))
+        return ops.conv3x3(x, pk["w"], self.conv.out_channels, bias=pk["b"], stride=2)
+
+
+class Upsample(nn.Module):
+    """Upsample3D / Upsample2D: nearest 2x + conv3x3 (reference src/models/resnet.py:32-91)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+        self._pk = PackedCache()
+
+    def run(self, x):
+        pk = self._pk.get(self, lambda: dict(w=ops.pack_conv3x3_weight(self.conv.weight.detach()), b=f32(self.conv.bias)))
+        return ops.conv3x3(ops.upsample2x(x), pk["w"], self.conv.out_channels, bias=pk["b"])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# spatial transformer (self / reference attention + constant cross-attention + GEGLU FF)
+# ------------------------------------------------------------------------------------------------------------
+class BasicTransformerBlock(nn.Module):
+    """Parameters of (Temporal)BasicTransformerBlock (reference src/models/attention.py:14-445) and the forward the
+    reference installs on it through ReferenceAttentionControl (src/models/mutual_self_attention.py:93-265).
+
+    `bank` / `_ref_mode` / `_ref_cfg` are managed by aniportrait_b200.models.mutual_self_attention."""
+
+    def __init__(self, dim, heads, dim_head, cross_attention_dim=768):
+        super().__init__()
+        self.dim, self.heads, self.dim_head = dim, heads, dim_head
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        if cross_attention_dim is not None:
+            self.norm2 = nn.LayerNorm(dim)
+            self.attn2 = Attention(dim, cross_attention_dim, heads, dim_head)
+        else:
+            self.norm2 = None
+            self.attn2 = None
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+        self.bank = []
+        self._ref_mode = None       # None | "write" | "read"
+        self._ref_cfg = False
+        self._pk = PackedCache()
+        self._bank_kv = None        # (key, [n_banks*N, 2*heads*dpad] fp16)
+        self._attn2_const = None    # (key, fp32 [B, dim])
+
+    def packed(self):
+        def build():
+            dpad = ops.head_pad(self.dim_head)
+            wq = ops.pad_head_rows(f16(self.attn1.to_q.weight), self.heads, dpad)
+            wk = ops.pad_head_rows(f16(self.attn1.to_k.weight), self.heads, dpad)
+            wv = ops.pad_head_rows(f16(self.attn1.to_v.weight), self.heads, dpad)
+            d = dict(dpad=dpad, wqkv=torch.cat([wq, wk, wv], 0).contiguous(), wkv=torch.cat([wk, wv], 0).contiguous(),
+                     wo=f16(self.attn1.to_out[0].weight), bo=f32(self.attn1.to_out[0].bias),
+                     g1=f32(self.norm1.weight), b1=f32(self.norm1.bias), g3=f32(self.norm3.weight),
+                     b3=f32(self.norm3.bias))
+            if self.attn2 is not None:
+                d.update(wv2=f16(self.attn2.to_v.weight), wo2=f16(self.attn2.to_out[0].weight),
+                         bo2=f32(self.attn2.to_out[0].bias))
+            return d
+        return self._pk.get(self, build)
+
+    def _attn_out_bias(self, pk, ctx: RunCtx):
+        """attn1 out bias (+ the attn2 term). With a single encoder token softmax == 1, so attn2's output is the
+        per-batch constant to_out(to_v(e)) + b, independent of the query (reference attention.py:339-347 runs the full
+        q / out GEMMs for it every step). Folded into the to_out epilogue bias of attn1."""
+        if self.attn2 is None:
+            return pk["bo"], 0
+        ehs = ctx.ehs
+        if ehs is None or ehs.shape[1] != 1:
+            raise NotImplementedError("attn2 with more than one encoder token is not part of the AniPortrait hot path")
+        key = (ctx.ehs_key, ehs.data_ptr(), ehs._version, id(pk))
+        if self._attn2_const is None or self._attn2_const[0] != key:
+            e = ehs.reshape(ehs.shape[0], -1).contiguous()
+            v = ops.gemm(e, pk["wv2"])
+            c = ops.gemm(v, pk["wo2"], bias=(pk["bo2"] + pk["bo"]), out_f32=True)
+            self._attn2_const = (key, c)
+        return self._attn2_const[1], 1
+
+    def _bank_projection(self, pk, n_tokens):
+        """K/V of the ReferenceNet bank under THIS block's to_k/to_v. The bank is step- and frame-invariant, so it is
+        projected once per video (the reference re-projects it for 16 frames x 25 steps)."""
+        bank = self.bank[0]
+        key = (bank.data_ptr(), bank._version, id(pk))
+        if self._bank_kv is None or self._bank_kv[0] != key:
+            nb = bank.shape[0]
+            kv = ops.gemm(bank.reshape(nb * bank.shape[1], bank.shape[2]).contiguous(), pk["wkv"])
+            self._bank_kv = (key, kv, nb)
+        return self._bank_kv[1], self._bank_kv[2]
+
+    def run(self, t0: torch.Tensor, n_frames: int, tokens: int, ctx: RunCtx) -> torch.Tensor:
+        """t0: [n_frames*tokens, dim] fp16."""
+        pk = self.packed()
+        dpad, heads, d = pk["dpad"], self.heads, self.dim_head
+        hp = heads * dpad
+        n1 = ops.layer_norm(t0, pk["g1"], pk["b1"])
+        if self._ref_mode == "write":
+            self.bank.append(n1.view(n_frames, tokens, self.dim).clone())
+        qkv = ops.gemm(n1, pk["wqkv"])
+        q, k, v = qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:]
+        kw = {}
+        if self._ref_mode == "read" and len(self.bank) > 0:
+            kv, nb = self._bank_projection(pk, tokens)
+            bank_tokens = self.bank[0].shape[1]
+            if self._ref_cfg:
+                # frames of the first half of the batch are the unconditional branch: no reference keys
+                # (mutual_self_attention.py:166-186); frame f of the second half reads bank[f // F] (:148-157)
+                first = (ctx.B // 2) * ctx.F
+                kw = dict(bank_k=kv[:, :hp], bank_v=kv[:, hp:], bank_tokens=bank_tokens, n_banks=nb,
+                          first_bank_frame=first, frames_per_bank=ctx.F)
+                if nb > 1:   # bank rows of the conditional half only
+                    nbh = nb // 2
+                    kw["bank_k"] = kv[nbh * bank_tokens:, :hp]
+                    kw["bank_v"] = kv[nbh * bank_tokens:, hp:]
+                    kw["n_banks"] = nb - nbh
+            else:
+                kw = dict(bank_k=kv[:, :hp], bank_v=kv[:, hp:], bank_tokens=bank_tokens, n_banks=nb,
+                          first_bank_frame=0, frames_per_bank=ctx.F)
+        a = ops.attention(q, k, v, n_frames, tokens, heads, d, dpad, **kw)
+        bias, grouped = self._attn_out_bias(pk, ctx)
+        t1 = ops.gemm(a, pk["wo"], bias=bias, residual=t0, bias_group_rows=(ctx.F * tokens if grouped else 0))
+        n3 = ops.layer_norm(t1, pk["g3"], pk["b3"])
+        return self.ff.run(n3, t1)
+
+
+class TemporalBasicTransformerBlock(BasicTransformerBlock):
+    """Same parameters/forward as BasicTransformerBlock; separate class name as in the reference
+    (src/models/attention.py:300) so reader/writer selection by type keeps working."""
+
+
+class SpatialTransformer(nn.Module):
+    """Transformer3DModel / Transformer2DModel with use_linear_projection=False (reference
+    src/models/transformer_3d.py:27-169): GroupNorm(eps 1e-6) -> 1x1 conv -> block -> 1x1 conv -> + residual."""
+
+    block_cls = BasicTransformerBlock
+
+    def __init__(self, heads, dim_head, in_channels, cross_attention_dim=768, groups=32):
+        super().__init__()
+        inner = heads * dim_head
+        self.in_channels, self.inner, self.groups = in_channels, inner, groups
+        self.norm = nn.GroupNorm(groups, in_channels, eps=1e-6)
+        self.proj_in = nn.Conv2d(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList([self.block_cls(inner, heads, dim_head, cross_attention_dim)])
+        self.proj_out = nn.Conv2d(inner, in_channels, 1)
+        self._pk = PackedCache()
+
+    def packed(self):
+        def build():
+            return dict(g=f32(self.norm.weight), b=f32(self.norm.bias),
+                        wi=f16(self.proj_in.weight.reshape(self.inner, self.in_channels)), bi=f32(self.proj_in.bias),
+                        wo=f16(self.proj_out.weight.reshape(self.in_channels, self.inner)), bo=f32(self.proj_out.bias))
+        return self._pk.get(self, build)
+
+    def run(self, x: torch.Tensor, ctx: RunCtx) -> torch.Tensor:
+        pk = self.packed()
+        nf, h, w, c = x.shape
+        hn = ops.group_norm(x, pk["g"], pk["b"], self.groups, 1e-6, False)
+        t0 = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"])
+        t = self.transformer_blocks[0].run(t0, nf, h * w, ctx)
+        out = ops.gemm(t, pk["wo"], bias=pk["bo"], residual=x.view(-1, c))
+        return out.view(nf, h, w, c)
+
+
+class Transformer3DModel(SpatialTransformer):
+    block_cls = TemporalBasicTransformerBlock
+
+
+class Transformer2DModel(SpatialTransformer):
+    block_cls = BasicTransformerBlock
+
+
+# ------------------------------------------------------------------------------------------------------------
+# motion module
+# ------------------------------------------------------------------------------------------------------------
+class PositionalEncoding(nn.Module):
+    """Sinusoidal buffer `pe` [1, max_len, d] (reference src/models/motion_module.py:262-277)."""
+
+    def __init__(self, d_model, max_len=32):
+        super().__init__()
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(1, max_len, d_model)
+        pe[0, :, 0::2] = torch.sin(position * div_term)
+        pe[0, :, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+
+class VersatileAttention(Attention):
+    def __init__(self, query_dim, heads, dim_head, max_len):
+        super().__init__(query_dim, None, heads, dim_head)
+        self.pos_encoder = PositionalEncoding(query_dim, max_len)
+
+
+class TemporalTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, max_len):
+        super().__init__()
+        self.attention_blocks = nn.ModuleList([VersatileAttention(dim, heads, dim_head, max_len) for _ in range(2)])
+        self.norms = nn.ModuleList([nn.LayerNorm(dim) for _ in range(2)])
+        self.ff = FeedForward(dim)
+        self.ff_norm = nn.LayerNorm(dim)
+
+
+class TemporalTransformer3DModel(nn.Module):
+    """TemporalTransformer3DModel (reference src/models/motion_module.py:94-182) with one TemporalTransformerBlock
+    (two Temporal_Self attentions + GEGLU FF)."""
+
+    def __init__(self, in_channels, heads=8, max_len=32, groups=32):
+        super().__init__()
+        self.channels, self.heads, self.groups, self.max_len = in_channels, heads, groups, max_len
+        self.norm = nn.GroupNorm(groups, in_channels, eps=1e-6)
+        self.proj_in = nn.Linear(in_channels, in_channels)
+        self.transformer_blocks = nn.ModuleList([TemporalTransformerBlock(in_channels, heads, in_channels // heads,
+                                                                          max_len)])
+        self.proj_out = nn.Linear(in_channels, in_channels)
+        self._pk = PackedCache()
+
+    def packed(self):
+        def build():
+            blk = self.transformer_blocks[0]
+            d = dict(g=f32(self.norm.weight), b=f32(self.norm.bias), wi=f16(self.proj_in.weight),
+                     bi=f32(self.proj_in.bias), wo=f16(self.proj_out.weight), bo=f32(self.proj_out.bias),
+                     gf=f32(blk.ff_norm.weight), bf=f32(blk.ff_norm.bias), attn=[])
+            for i in range(2):
+                at = blk.attention_blocks[i]
+                d["attn"].append(dict(
+                    wqkv=torch.cat([f16(at.to_q.weight), f16(at.to_k.weight), f16(at.to_v.weight)], 0).contiguous(),
+                    wo=f16(at.to_out[0].weight), bo=f32(at.to_out[0].bias), g=f32(blk.norms[i].weight),
+                    b=f32(blk.norms[i].bias),
+                    # the reference adds the (fp16) buffer to the LayerNorm output: keep its rounding
+                    pe=at.pos_encoder.pe[0].detach().to(torch.float16).to(torch.float32).contiguous()))
+            return d
+        return self._pk.get(self, build)
+
+    def run(self, x: torch.Tensor, ctx: RunCtx) -> torch.Tensor:
+        pk = self.packed()
+        nf, h, w, c = x.shape
+        n_tok = h * w
+        if ctx.F > self.max_len:
+            raise ValueError(f"window of {ctx.F} frames exceeds temporal_position_encoding_max_len={self.max_len}")
+        hn = ops.group_norm(x, pk["g"], pk["b"], self.groups, 1e-6, False)
+        m = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"])
+        for i in range(2):
+            a = pk["attn"][i]
+            n = ops.layer_norm(m, a["g"], a["b"], pe=a["pe"], rows_per_pe=n_tok, pe_period=ctx.F)
+            qkv = ops.gemm(n, a["wqkv"])
+            o = ops.temporal_attention(qkv, ctx.B, ctx.F, n_tok, c, self.heads)
+            m = ops.gemm(o, a["wo"], bias=a["bo"], residual=m)
+        n = ops.layer_norm(m, pk["gf"], pk["bf"])
+        m = self.transformer_blocks[0].ff.run(n, m)
+        out = ops.gemm(m, pk["wo"], bias=pk["bo"], residual=x.view(-1, c))
+        return out.view(nf, h, w, c)
+
+
+class VanillaTemporalModule(nn.Module):
+    """motion_modules.N = VanillaTemporalModule(temporal_transformer=...) (reference motion_module.py:44-91)."""
+
+    def __init__(self, in_channels, num_attention_heads=8, temporal_position_encoding_max_len=32, **_):
+        super().__init__()
+        self.temporal_transformer = TemporalTransformer3DModel(in_channels, num_attention_heads,
+                                                               temporal_position_encoding_max_len)
+
+    def run(self, x, ctx):
+        return self.temporal_transformer.run(x, ctx)

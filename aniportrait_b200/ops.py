@@ -60,7 +60,7 @@ def interleave_geglu(w: torch.Tensor, b: torch.Tensor | None):
 # --------------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
          a2: torch.Tensor | None = None, geglu: bool = False, out: torch.Tensor | None = None,
-         bias_group_rows: int = 0, n_valid: int = 0, block_n: int = 0) -> torch.Tensor:
+         bias_group_rows: int = 0, n_valid: int = 0, block_n: int = 0, out_f32: bool = False) -> torch.Tensor:
     """out = [a | a2] @ w.T (+bias) (+residual); a:[M,K1] fp16 (row stride may exceed K1), w:[N,K1+K2] fp16."""
     _ensure(a)
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and w.dim() == 2
@@ -76,8 +76,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
     if n_valid:
         nout = n_valid
     if out is None:
-        out = torch.empty(M, nout, dtype=torch.float16, device=a.device)
-    assert out.stride(1) == 1
+        out = torch.empty(M, nout, dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
+    assert out.stride(1) == 1 and out.dtype == (torch.float32 if out_f32 else torch.float16)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape[-1] == N
     if residual is not None:
@@ -85,7 +85,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
     rc = lib().ap_gemm_f16(ptr(a), LL(a.stride(0)), I(K1), ptr(a2), LL(a2.stride(0) if a2 is not None else 0), I(K2),
                            ptr(w), LL(M), I(N), fptr(bias), LL(bias_group_rows), ptr(residual),
                            LL(residual.stride(0) if residual is not None else 0), ptr(out), LL(out.stride(0)),
-                           I(nout), I(1 if geglu else 0), I(block_n), stream_ptr())
+                           I(nout), I((1 if geglu else 0) | (2 if out_f32 else 0)), I(block_n), stream_ptr())
     check(rc, "ap_gemm_f16")
     _count()
     return out
@@ -250,6 +250,29 @@ def add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> to
     if out is None:
         out = torch.empty_like(a)
     check(lib().ap_add_f16(ptr(a), ptr(b), ptr(out), LL(a.numel()), stream_ptr()), "ap_add_f16")
+    _count()
+    return out
+
+
+def add_bcast(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """a: [dup*n...], b: [n...] broadcast over the leading duplicate (CFG) dimension."""
+    _ensure(a)
+    assert a.dtype == torch.float16 and a.is_contiguous() and b.is_contiguous() and a.numel() % b.numel() == 0
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().ap_add_bcast_f16(ptr(a), ptr(b), ptr(out), LL(a.numel()), LL(b.numel()), stream_ptr()),
+          "ap_add_bcast_f16")
+    _count()
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """t: fp32 [B] on device -> fp16 [B, dim] (cos | sin)."""
+    _ensure(t)
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty(t.numel(), dim, dtype=torch.float16, device=t.device)
+    check(lib().ap_timestep_embedding_f16(fptr(t), I(t.numel()), I(dim), ptr(out), stream_ptr()),
+          "ap_timestep_embedding_f16")
     _count()
     return out
 

@@ -29,6 +29,7 @@ extern "C" {
 
 /* flags for ap_gemm_f16 */
 #define AP_GEMM_GEGLU 1 /* weight rows interleaved [16 value | 16 gate]; out = value * gelu_erf(gate), N/2 columns */
+#define AP_GEMM_OUT_F32 2 /* `out` is fp32 [M, ldo] (used for the small per-step bias tables) */
 
 int ap_version(void);
 const char* ap_last_error(void);
@@ -104,6 +105,10 @@ int ap_temporal_attention_f16(const void* qkv, long long ld, void* out, long lon
 /* Elementwise / layout helpers (fp16, n % 8 == 0 where vectorised). */
 int ap_add_f16(const void* a, const void* b, void* out, long long n, void* stream);          /* unet_3d.py:485-486,508-510 */
 int ap_silu_f16(const void* x, void* out, long long n, void* stream);                        /* resnet.py:226-230 */
+/* out[i] = a[i] + b[i % nb] (b broadcast over the leading CFG-branch dim) */
+int ap_add_bcast_f16(const void* a, const void* b, void* out, long long n, long long nb, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t_b w_i) | sin(t_b w_i)], unet_3d.py:463 */
+int ap_timestep_embedding_f16(const float* t, int B, int dim, void* out, void* stream);
 int ap_upsample2x_nhwc_f16(const void* x, void* out, int Nf, int H, int W, int C, void* stream); /* resnet.py:71-78 */
 int ap_ncfhw_to_nhwc_f16(const void* x, void* out, int B, int C, int F, int HW, int Cpad, void* stream);
 int ap_nhwc_to_ncfhw_f16(const void* x, void* out, int B, int C, int F, int HW, int ld, void* stream);
