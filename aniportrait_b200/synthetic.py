@@ -13,21 +13,21 @@ def randomize_state_dict(sd: dict, seed: int = 0, std: float = 0.02) -> dict:
     out = {}
     for name, t in sd.items():
         if name.endswith(".pe"):  # positional-encoding buffers keep their analytic values
-            out[name] = t
+            out[name] = _sinusoid_pe(t.shape[1], t.shape[2]).to(t.dtype) if t.is_meta else t
             continue
         if not t.is_floating_point():
-            out[name] = t
+            out[name] = torch.zeros(t.shape, dtype=t.dtype) if t.is_meta else t
             continue
         leaf = name.rsplit(".", 1)[-1]
         is_norm = any(k in name for k in (".norm", "norm1", "norm2", "norm3", "ff_norm", "norms.", "group_norm",
                                           "conv_norm_out"))
         is_bn = t.dim() == 1 and ("conv_layers" in name)
         if name == "scale":
-            v = torch.full_like(t, 2.0)
+            v = torch.full(t.shape, 2.0)
         elif "running_mean" in name:
-            v = torch.zeros_like(t)
+            v = torch.zeros(t.shape)
         elif "running_var" in name:
-            v = torch.ones_like(t)
+            v = torch.ones(t.shape)
         elif (is_norm or (is_bn and leaf == "weight" and t.dim() == 1 and _is_bn_name(name, sd))) and leaf == "weight":
             v = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
         elif leaf == "bias":
@@ -37,6 +37,21 @@ def randomize_state_dict(sd: dict, seed: int = 0, std: float = 0.02) -> dict:
             v = torch.randn(t.shape, generator=g) * min(std * 2.5, 1.0 / math.sqrt(max(fan_in, 1)))
         out[name] = v.to(t.dtype)
     return out
+
+
+def _sinusoid_pe(max_len, d_model):
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def meta_state_dict(factory):
+    """Shapes/dtypes of a model's state dict without allocating or initialising it."""
+    with torch.device("meta"):
+        return factory().state_dict()
 
 
 def _is_bn_name(name, sd):

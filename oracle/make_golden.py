@@ -63,13 +63,85 @@ def case_unet3d(name, chans, Fr, h, w, timestep, seeds=(101, 102, 103)):
         out = unet3d(sample, torch.tensor(timestep), encoder_hidden_states=ehs, pose_cond_fea=pose,
                      return_dict=False)[0]
     torch.save(dict(case=name, chans=tuple(chans), frames=Fr, h=h, w=w, timestep=timestep, seeds=tuple(seeds),
-                    out=out.float().contiguous(), torch_version=torch.__version__,
+                    out=out.float().contiguous(), torch_version=str(torch.__version__),
                     generator="reference src/models via oracle/diffusers_shim, fp32 CPU"),
                os.path.join(GOLDEN, name + ".pt"))
     print(f"{name}: out {tuple(out.shape)} |out|={out.norm():.4f} in {time.time() - t0:.1f}s")
 
 
+PIPE_SMALL = dict(chans=(64, 128, 256, 256), vae_chans=(32, 64, 128, 128), size=128, L=20, steps=3, guidance=3.5,
+                  seeds=dict(unet3d=301, unet2d=302, pose=303, vae=304, clip=305, inputs=306, latents=42))
+SCHED_KWARGS = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+                    prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+
+
+def small_clip_encoder(seed):
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                           image_size=224, patch_size=32, projection_dim=768)
+    torch.manual_seed(seed)
+    m = CLIPVisionModelWithProjection(cfg)
+    m.load_state_dict(randomize_state_dict(m.state_dict(), seed=seed))
+    return m.eval()
+
+
+def pipeline_inputs(size, L, seed):
+    """Synthetic reference image (PIL RGB) and pose maps (uint8 HxWx3 arrays with a few coloured segments), as the
+    scripts pass them (scripts/pose2vid.py:120-176)."""
+    import numpy as np
+    import PIL.Image
+    rng = np.random.RandomState(seed)
+    ref_image = PIL.Image.fromarray(rng.randint(0, 256, (size + 40, size + 24, 3), dtype=np.uint8))
+
+    def pose_map(r):
+        img = np.zeros((size, size, 3), dtype=np.uint8)
+        for _ in range(24):
+            x0, y0 = r.randint(0, size, 2)
+            ln = r.randint(4, size // 3)
+            col = r.randint(64, 256, 3)
+            if r.rand() < 0.5:
+                img[y0:y0 + 2, x0:min(size, x0 + ln)] = col
+            else:
+                img[y0:min(size, y0 + ln), x0:x0 + 2] = col
+        return img
+
+    poses = [pose_map(np.random.RandomState(seed + 1 + f)) for f in range(L)]
+    ref_pose = pose_map(np.random.RandomState(seed + 1000))
+    return ref_image, poses, ref_pose
+
+
+def case_pipeline(name="pipeline_small", P=PIPE_SMALL):
+    """Whole Pose2VideoPipeline.__call__ of the reference (pipeline_pose2vid_long.py:338-584): CLIP -> ReferenceNet ->
+    windowed CFG/DDIM loop with in-loop PoseGuider -> frame-wise VAE decode. Two overlapping 16-frame windows."""
+    ref_import.activate()
+    from diffusers import AutoencoderKL, DDIMScheduler
+    from src.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline
+    t0 = time.time()
+    sd = P["seeds"]
+    unet3d = ref_import.build_unet3d(P["chans"]); _load(unet3d, sd["unet3d"])
+    unet2d = ref_import.build_unet2d(P["chans"]); _load(unet2d, sd["unet2d"])
+    pose = ref_import.build_pose_guider(P["chans"][0]); _load(pose, sd["pose"])
+    vae = AutoencoderKL(block_out_channels=P["vae_chans"]); _load(vae, sd["vae"])
+    clip = small_clip_encoder(sd["clip"])
+    pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=unet2d, denoising_unet=unet3d,
+                              pose_guider=pose, scheduler=DDIMScheduler(**SCHED_KWARGS))
+    ref_image, poses, ref_pose = pipeline_inputs(P["size"], P["L"], sd["inputs"])
+    lat_trace = []
+    out = pipe(ref_image, poses, ref_pose, P["size"], P["size"], P["L"], P["steps"], P["guidance"],
+               generator=torch.manual_seed(sd["latents"]), callback=lambda i, t, l: lat_trace.append(l.clone()),
+               callback_steps=1)
+    videos = out.videos
+    torch.save(dict(case=name, params={k: v for k, v in P.items()}, final_latents=lat_trace[-1].float(),
+                    first_step_latents=lat_trace[0].float(), video_frames=videos[:, :, [0, 7, P["L"] - 1]].half(),
+                    video_mean=float(videos.mean()), torch_version=str(torch.__version__),
+                    generator="reference Pose2VideoPipeline via oracle/diffusers_shim, fp32 CPU"),
+               os.path.join(GOLDEN, name + ".pt"))
+    print(f"{name}: videos {tuple(videos.shape)} mean={videos.mean():.4f} steps traced={len(lat_trace)} "
+          f"in {time.time() - t0:.1f}s")
+
+
 CASES = {
+    "pipeline_small": case_pipeline,
     # full SD1.5 width (the real model size), 256x256-pixel equivalent latents, 4-frame window
     "unet3d_full_f4_32x32": lambda: case_unet3d("unet3d_full_f4_32x32", (320, 640, 1280, 1280), 4, 32, 32, 479),
     # reduced width, 16-frame window (temporal attention at the production window length), non-square latent

@@ -66,6 +66,24 @@ with torch.no_grad():
     torch.cuda.synchronize()
     tw = time.time() - tw
 ms = e0.elapsed_time(e1) / iters
+if os.environ.get("GRAPH", "1") == "1":
+    tt = torch.tensor([500.0], device=dev)
+    with torch.no_grad():
+        sstream = torch.cuda.Stream()
+        with torch.cuda.stream(sstream):
+            out = unet3d.forward_nhwc(x, 2, F, tt, ehs, pose)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = unet3d.forward_nhwc(x, 2, F, tt, ehs, pose)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for it in range(iters):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    print(f"CUDA-graph replay: {e0.elapsed_time(e1) / iters:.2f} ms per UNet call")
 flops = 36.43e12 * (F / 16) * (H / 64) ** 2
 print(f"UNet3D call F={F} {H}x{H}: {ms:.2f} ms (wall {tw / iters * 1e3:.2f} ms), launches/call={(ops.KERNEL_LAUNCHES - n0) // iters}, "
       f"{flops / ms / 1e9:.1f} TFLOP/s algorithmic, finite={torch.isfinite(out.float()).all().item()}, "

@@ -56,3 +56,62 @@ def seeded_inputs_unet3d(B, Fr, h, w, chans, seed):
     sizes = [(chans[0], h), (chans[0], h // 2), (chans[1], h // 4), (chans[2], h // 8), (chans[3], h // 8)]
     pose = [0.5 * torch.randn(1, c, Fr, s, s * w // h, generator=g).repeat(B, 1, 1, 1, 1) for c, s in sizes]
     return sample, ehs, ref_lat, pose
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole-pipeline fixtures (must stay identical to oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------
+SCHED_KWARGS = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+                    prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+
+
+def small_clip_encoder(seed):
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                           image_size=224, patch_size=32, projection_dim=768)
+    torch.manual_seed(seed)
+    m = CLIPVisionModelWithProjection(cfg)
+    m.load_state_dict(randomize_state_dict(m.state_dict(), seed=seed))
+    return m.eval()
+
+
+def pipeline_inputs(size, L, seed):
+    import numpy as np
+    import PIL.Image
+    rng = np.random.RandomState(seed)
+    ref_image = PIL.Image.fromarray(rng.randint(0, 256, (size + 40, size + 24, 3), dtype=np.uint8))
+
+    def pose_map(r):
+        img = np.zeros((size, size, 3), dtype=np.uint8)
+        for _ in range(24):
+            x0, y0 = r.randint(0, size, 2)
+            ln = r.randint(4, size // 3)
+            col = r.randint(64, 256, 3)
+            if r.rand() < 0.5:
+                img[y0:y0 + 2, x0:min(size, x0 + ln)] = col
+            else:
+                img[y0:min(size, y0 + ln), x0:x0 + 2] = col
+        return img
+
+    poses = [pose_map(np.random.RandomState(seed + 1 + f)) for f in range(L)]
+    ref_pose = pose_map(np.random.RandomState(seed + 1000))
+    return ref_image, poses, ref_pose
+
+
+def build_pipeline(P, device):
+    """Product Pose2VideoPipeline with the seeded weights of golden case `P` (params dict of the fixture)."""
+    from aniportrait_b200.models.pose_guider import PoseGuider
+    from aniportrait_b200.models.vae import AutoencoderKL
+    from aniportrait_b200.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline
+    from aniportrait_b200.pipelines.scheduler import DDIMScheduler
+    sd = P["seeds"]
+    unet3d, _ = build_unet3d(P["chans"], sd["unet3d"])
+    unet2d, _ = build_unet2d(P["chans"], sd["unet2d"])
+    pose = PoseGuider(P["chans"][0])
+    pose.load_state_dict(randomize_state_dict(pose.state_dict(), seed=sd["pose"]))
+    vae = AutoencoderKL(block_out_channels=tuple(P["vae_chans"]))
+    vae.load_state_dict(randomize_state_dict(vae.state_dict(), seed=sd["vae"]))
+    clip = small_clip_encoder(sd["clip"])
+    pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=unet2d, denoising_unet=unet3d,
+                              pose_guider=pose, scheduler=DDIMScheduler(**SCHED_KWARGS))
+    return pipe.to(device, dtype=torch.float16)
