@@ -253,17 +253,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int jj = own ? j : j - own_tiles;
         const int ntok = own ? p.tokens : p.bank_tokens;
         const int valid = min(BN, ntok - jj * BN);
-        float tmax = -INFINITY;
-        if (valid == BN) {
+        if (valid != BN) {
 #pragma unroll
-          for (int i = 0; i < BN; ++i) tmax = fmaxf(tmax, __uint_as_float(sr[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < BN; ++i) {
+          for (int i = 0; i < BN; ++i)
             if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
-            tmax = fmaxf(tmax, __uint_as_float(sr[i]));
-          }
         }
+        // row max with 8 independent chains (a single 128-long fmax chain costs ~4 clk per element)
+        float mx8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+#pragma unroll
+        for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sr[i]));
+        float tmax = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                           fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         tmax *= p.scale_log2;
         float alpha = 1.f;
         bool need = false;
@@ -279,16 +281,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
         // P = exp2(S*c - m), packed to fp16 pairs; row sum in fp32
         uint32_t pk[BN / 2];
-        float lsum = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < BN; i += 2) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
           const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
-          lsum += p0 + p1;
+          ls[(i >> 1) & 3] += p0 + p1;
           const __half2 h = __floats2half2_rn(p0, p1);
           pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        l_run += lsum;
+        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
 
         // previous P.V must have completed before P is overwritten / O is rescaled
         if (g > 0) mbar_wait(pv_done, (g - 1) & 1);

@@ -57,6 +57,25 @@ class ModelBase(nn.Module):
             return json.load(f)
 
     @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, **kwargs):
+        """diffusers-style loader: <path>/<subfolder>/config.json + diffusion_pytorch_model.{safetensors,bin}
+        (scripts/pose2vid.py:59-64)."""
+        import os
+        path = os.path.join(str(pretrained_model_path), subfolder) if subfolder else str(pretrained_model_path)
+        model = cls.from_config(cls.load_config(os.path.join(path, cls.config_name)), **kwargs)
+        st = os.path.join(path, "diffusion_pytorch_model.safetensors")
+        pt = os.path.join(path, "diffusion_pytorch_model.bin")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st, device="cpu")
+        elif os.path.exists(pt):
+            sd = torch.load(pt, map_location="cpu", weights_only=True)
+        else:
+            raise FileNotFoundError(f"no weights file found in {path}")
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    @classmethod
     def from_config(cls, config, **kwargs):
         sig = inspect.signature(cls.__init__).parameters
         init = {k: v for k, v in dict(config).items() if k in sig and not k.startswith("_")}

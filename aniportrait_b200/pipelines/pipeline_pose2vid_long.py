@@ -24,7 +24,7 @@ import torch
 
 from .. import ops
 from ..models.mutual_self_attention import ReferenceAttentionControl
-from .context import get_context_scheduler
+from .sharding import plan_windows, windows_of_rank
 from .image_processor import VaeImageProcessor
 
 
@@ -54,6 +54,7 @@ class Pose2VideoPipeline:
         self.cond_image_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor, do_convert_rgb=True,
                                                       do_normalize=True)
         self.timings = {}
+        self.use_cuda_graph = True   # capture the per-window UNet step once, replay it every DDIM step
 
     # -------------------------------------------------------------------------------------------- plumbing
     def _nn_modules(self):
@@ -191,31 +192,55 @@ class Pose2VideoPipeline:
 
         # pose maps -> PoseGuider, once per window ------------------------------------------------------------
         pose_cond = pose_cond.to(device=device, dtype=self.pose_guider.dtype)
-        windows = list(get_context_scheduler(context_schedule)(0, num_inference_steps, L, context_frames,
-                                                                context_stride, context_overlap))
+        windows, inv_count = plan_windows(L, num_inference_steps, context_schedule, context_frames, context_stride,
+                                          context_overlap)
         shard = world > 1 and dist_mode == "windows"
-        my_windows = [wd for i, wd in enumerate(windows) if (i % world == rank or not shard)]
+        my_windows = windows_of_rank(windows, rank, world, shard)
         win_idx = [torch.tensor(wd, dtype=torch.int32, device=device) for wd in my_windows]
         win_pose = []
         for wd in my_windows:
             fea = self.pose_guider.forward_nhwc(pose_cond[wd])
             win_pose.append([f.to(torch.float16).contiguous() for f in fea])
-        counts = torch.zeros(L)
-        for wd in windows:
-            for f in wd:
-                counts[f] += 1
-        inv_count = (1.0 / counts).to(device=device, dtype=torch.float32)
+        inv_count = inv_count.to(device=device, dtype=torch.float32)
         acc = torch.zeros(dup, L, h, w, 4, dtype=torch.float32, device=device)
 
         # denoising loop -----------------------------------------------------------------------------------------
+        # Shapes are static, so the per-window work (gather -> ~800 kernel launches of the UNet -> scatter-accumulate)
+        # is captured once in a CUDA graph per window and replayed every step; only the timestep buffer changes.
+        t_dev = torch.zeros(1, dtype=torch.float32, device=device)
+
+        def window_step(idx, pose_fea):
+            x = ops.gather_window(lat, idx, dup, 64)
+            pred = self.denoising_unet.forward_nhwc(x, dup, idx.numel(), t_dev, ehs, pose_fea)
+            ops.scatter_accumulate(pred, idx, acc)
+
+        graphs = []
+        if self.use_cuda_graph and len(win_idx) > 0:
+            t_dev.fill_(float(timesteps[0]))
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                window_step(win_idx[0], win_pose[0])       # warm-up: one-time caches, kernel attributes, workspaces
+                acc.zero_()
+            torch.cuda.current_stream(device).wait_stream(side)
+            pool = None
+            for idx, pose_fea in zip(win_idx, win_pose):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=side):
+                    window_step(idx, pose_fea)
+                pool = g.pool()
+                graphs.append(g)
+            acc.zero_()
         ev[1].record()
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
-                t_dev = torch.full((1,), float(t), dtype=torch.float32, device=device)
-                for idx, pose_fea in zip(win_idx, win_pose):
-                    x = ops.gather_window(lat, idx, dup, 64)
-                    pred = self.denoising_unet.forward_nhwc(x, dup, idx.numel(), t_dev, ehs, pose_fea)
-                    ops.scatter_accumulate(pred, idx, acc)
+                t_dev.fill_(float(t))
+                if graphs:
+                    for g in graphs:
+                        g.replay()
+                else:
+                    for idx, pose_fea in zip(win_idx, win_pose):
+                        window_step(idx, pose_fea)
                 if shard:
                     torch.distributed.all_reduce(acc)
                 a_t, a_p = self._alpha_pair(t)

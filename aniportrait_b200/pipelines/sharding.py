@@ -1,0 +1,50 @@
+"""Host-side work partitioning of the denoising loop. Pure Python / CPU torch: unit-testable with gloo.
+
+Within one DDIM step every context window is an independent UNet call (reference pipeline_pose2vid_long.py:519-548);
+their predictions are summed per frame, divided by the per-frame window count, CFG-combined and stepped. Sharding the
+windows over ranks therefore needs exactly one sum-all-reduce of the fp32 accumulator per step."""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from .context import get_context_scheduler
+
+
+def plan_windows(num_frames: int, num_inference_steps: int, context_schedule="uniform", context_frames=16,
+                 context_stride=1, context_overlap=4):
+    """Window list (frame indices, wrap-around) and per-frame 1/count, as the reference computes them every step with
+    step=0 (so they are step-invariant)."""
+    windows = list(get_context_scheduler(context_schedule)(0, num_inference_steps, num_frames, context_frames,
+                                                           context_stride, context_overlap))
+    counts = torch.zeros(num_frames)
+    for wd in windows:
+        for f in wd:
+            counts[f] += 1
+    if (counts == 0).any():
+        raise ValueError("context schedule leaves frames uncovered")
+    return windows, 1.0 / counts
+
+
+def windows_of_rank(windows: List[List[int]], rank: int, world: int, shard: bool) -> List[List[int]]:
+    """Static round-robin assignment (every rank must derive the same plan without communication)."""
+    if not shard or world == 1:
+        return list(windows)
+    return [wd for i, wd in enumerate(windows) if i % world == rank]
+
+
+def accumulate(acc: torch.Tensor, pred: torch.Tensor, window: List[int]):
+    """CPU reference of ap_scatter_accumulate_f16: acc[b, window[f]] += pred[b, f] (acc fp32 [B, L, ...])."""
+    for j, f in enumerate(window):
+        acc[:, f] += pred[:, j].to(acc.dtype)
+    return acc
+
+
+def combine(acc: torch.Tensor, inv_count: torch.Tensor, guidance: float):
+    """Overlap average + classifier-free guidance (reference :551-555). acc [B, L, ...] -> [L, ...]."""
+    shape = [1, -1] + [1] * (acc.dim() - 2)
+    avg = acc * inv_count.view(*shape)
+    if acc.shape[0] == 2:
+        return avg[0] + guidance * (avg[1] - avg[0])
+    return avg[0]

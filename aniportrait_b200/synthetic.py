@@ -3,15 +3,18 @@ weights, zero biases, unit norm scales, PoseGuider scale 2, sinusoidal PE buffer
 from __future__ import annotations
 
 import math
+import zlib
 
 import torch
 
 
 def randomize_state_dict(sd: dict, seed: int = 0, std: float = 0.02) -> dict:
-    """Deterministically re-initialise a state dict in place (CPU generator; name order = dict order)."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    """Deterministically re-initialise a state dict. Every tensor draws from its own CPU generator seeded by
+    (seed, crc32(name)), so the values do not depend on the key ORDER (the reference's modules register their children
+    in a different order than ours, same keys)."""
     out = {}
     for name, t in sd.items():
+        g = torch.Generator(device="cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFF)
         if name.endswith(".pe"):  # positional-encoding buffers keep their analytic values
             out[name] = _sinusoid_pe(t.shape[1], t.shape[2]).to(t.dtype) if t.is_meta else t
             continue

@@ -343,7 +343,7 @@ def run_product(args):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU baseline (the reference's math restated in oracle/functional.py, fp32, host cores)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(threads=None, frames=2, latent=32):
+def cpu_baseline_sample(threads=None, frames=1, latent=16):
     """Bounded sample of the same workload on the host CPU: full-width UNet3D (1.31 B params, fp32) for ONE CFG DDIM step
     of a `frames`-frame window at latent `latent`x`latent` with reference attention + in-loop PoseGuider, exactly as
     the reference executes it; extrapolated linearly in (frames x pixels x steps) to 512x512 / L=16 / 25 steps."""
@@ -351,7 +351,7 @@ def cpu_baseline_sample(threads=None, frames=2, latent=32):
     from aniportrait_b200.models import UNet2DConditionModel, UNet3DConditionModel
     from aniportrait_b200.models.pose_guider import PoseGuider
     from oracle import functional as OF
-    threads = threads or os.cpu_count() or 1
+    threads = threads or min(os.cpu_count() or 1, 32)   # torch CPU conv/GEMM stops scaling (and oversubscribes) beyond ~32
     torch.set_num_threads(threads)
     t_build = time.perf_counter()
     sd3 = randomize_state_dict(meta_state_dict(lambda: UNet3DConditionModel(
@@ -390,7 +390,7 @@ def run_reference(args):
     unmodified reference wiring) on all host cores. Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    threads = args.cpu_threads or os.cpu_count() or 1
+    threads = args.cpu_threads or min(os.cpu_count() or 1, 32)
     vals = []
     for _ in range(max(1, min(args.steps, 2))):
         vals.append(cpu_baseline_sample(threads))

@@ -315,7 +315,8 @@ class DDIM:
         abar_sqrt = (abar_sqrt - aT) * (a0 / (a0 - aT))
         abar = abar_sqrt ** 2
         alphas = torch.cat([abar[0:1], abar[1:] / abar[:-1]])
-        self.alphas_cumprod = torch.cumprod(alphas, 0)
+        betas = 1 - alphas                                   # diffusers stores betas, then alphas = 1 - betas
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, 0)
         self.num_train = num_train
 
     def timesteps(self, n):

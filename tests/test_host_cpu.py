@@ -1,0 +1,169 @@
+"""CPU-only tests (-m "not gpu"): C-ABI library loads and exports every declared symbol; host-side logic (scheduler,
+window scheduler, image pre-processing, weight repacking, state-dict surface) against the oracle; world_size-2 gloo test
+of the window-sharded denoising step."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import functional as OF  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    from aniportrait_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = _lib.lib()
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 17
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/aniportrait_b200.h but not exported"
+    assert lib.ap_version() == 100
+
+
+def test_ops_refuse_cpu_tensors():
+    from aniportrait_b200 import _lib, ops
+    with pytest.raises(_lib.ApError):
+        ops.gemm(torch.zeros(128, 64, dtype=torch.float16), torch.zeros(64, 64, dtype=torch.float16))
+
+
+def test_product_forward_fails_loudly_without_gpu():
+    from helpers import build_unet3d
+    unet, _ = build_unet3d((64, 128, 256, 256), 1)
+    with pytest.raises(Exception):
+        unet(torch.zeros(1, 4, 2, 16, 16), 10, encoder_hidden_states=torch.zeros(1, 1, 768))
+
+
+def test_scheduler_matches_oracle():
+    from aniportrait_b200.pipelines.scheduler import DDIMScheduler
+    s = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
+                      prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")
+    o = OF.DDIM()
+    for n in (10, 25, 50):
+        s.set_timesteps(n)
+        assert s.timesteps.tolist() == o.timesteps(n)
+    s.set_timesteps(25)
+    assert torch.allclose(s.alphas_cumprod, o.alphas_cumprod, rtol=0, atol=0)
+    assert s.alphas_cumprod[-1].item() == 0.0   # zero terminal SNR
+    g = torch.Generator().manual_seed(0)
+    x, v = torch.randn(1, 4, 3, 8, 8, generator=g), torch.randn(1, 4, 3, 8, 8, generator=g)
+    for t in (999, 519, 39):
+        assert torch.allclose(s.step(v, t, x).prev_sample, o.step(v, t, x, 25), atol=1e-6)
+    a_t, a_p = s.alpha_pair(39)
+    assert a_p == 1.0 and 0 < a_t < 1
+
+
+@pytest.mark.parametrize("n", [1, 4, 16, 17, 24, 40, 128])
+def test_window_scheduler_matches_oracle(n):
+    from aniportrait_b200.pipelines.context import uniform
+    from aniportrait_b200.pipelines.sharding import plan_windows
+    assert list(uniform(0, 25, n, 16, 1, 4)) == OF.context_windows(n, 16, 4)
+    windows, inv = plan_windows(n, 25)
+    assert inv.shape == (n,) and (inv > 0).all()
+    if n == 128:
+        assert len(windows) == 11 and windows[-1] == list(range(120, 128)) + list(range(0, 8))
+
+
+def test_image_processor_paths():
+    import PIL.Image
+    from aniportrait_b200.pipelines.image_processor import VaeImageProcessor
+    p = VaeImageProcessor(vae_scale_factor=8, do_convert_rgb=True, do_normalize=True)
+    img = PIL.Image.fromarray(np.random.RandomState(0).randint(0, 256, (70, 90, 3), dtype=np.uint8))
+    t = p.preprocess(img, height=64, width=64)
+    assert t.shape == (1, 3, 64, 64) and -1.0 <= t.min() and t.max() <= 1.0
+    arr = np.zeros((64, 64, 3), dtype=np.uint8)
+    arr[10, 10] = 255
+    t = p.preprocess(arr, height=64, width=64)   # numpy path: NOT divided by 255 (diffusers 0.24 behaviour)
+    assert t.shape == (1, 3, 64, 64) and t.max().item() == 509.0 and t.min().item() == -1.0
+
+
+def test_weight_repacking():
+    from aniportrait_b200 import ops
+    w = torch.randn(10, 4, 3, 3)
+    wp = ops.pack_conv3x3_weight(w)
+    assert wp.shape == (32, 9 * 64)
+    v = wp.view(32, 3, 3, 64)
+    assert torch.equal(v[:10, :, :, :4], w.permute(0, 2, 3, 1).half()) and v[10:].abs().sum() == 0
+    wg, bg = ops.interleave_geglu(torch.arange(64 * 8).float().view(64, 8), torch.arange(64).float())
+    assert bg[:16].tolist() == list(range(16)) and bg[16:32].tolist() == list(range(32, 48))
+    wq = ops.pad_head_rows(torch.ones(8 * 40, 16), 8, 64)
+    assert wq.shape == (512, 16) and wq.view(8, 64, 16)[:, 40:].abs().sum() == 0
+    assert [ops.head_pad(d) for d in (8, 40, 80, 88, 160)] == [64, 64, 128, 128, 192]
+
+
+def test_reference_attention_control_pairing():
+    """update() pairs reader/writer blocks positionally after the stable width sort; clear() empties banks."""
+    from helpers import build_unet2d, build_unet3d
+    from aniportrait_b200.models import ReferenceAttentionControl
+    u3, _ = build_unet3d((64, 128, 256, 256), 1)
+    u2, _ = build_unet2d((64, 128, 256, 256), 2)
+    w = ReferenceAttentionControl(u2, mode="write", do_classifier_free_guidance=True, fusion_blocks="full")
+    r = ReferenceAttentionControl(u3, mode="read", do_classifier_free_guidance=True, fusion_blocks="full")
+    wm, rm = w._modules(u2), r._modules(u3)
+    assert len(wm) == len(rm) == 16
+    assert [m.norm1.normalized_shape[0] for m in rm] == [256] * 6 + [128] * 5 + [64] * 5
+    for i, m in enumerate(wm):
+        m.bank.append(torch.full((2, 4, m.norm1.normalized_shape[0]), float(i)))
+    r.update(w)
+    for i, m in enumerate(rm):
+        assert m.bank[0].dtype == torch.float16 and m.bank[0].flatten()[0].item() == float(i)
+        assert m._ref_mode == "read" and m._ref_cfg
+    r.clear()
+    assert all(len(m.bank) == 0 for m in rm)
+
+
+def _gloo_worker(rank, world, port, L, out_q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from aniportrait_b200.pipelines.sharding import accumulate, combine, plan_windows, windows_of_rank
+    windows, inv = plan_windows(L, 25)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, L, 4, 4, generator=g)
+
+    def fake_unet(x):   # deterministic stand-in for the UNet call of one window: [2, 4, F, h, w]
+        return torch.stack([torch.sin(x[0] * 1.3), torch.cos(x[0] * 0.7)]) + x.mean(dim=2, keepdim=True)
+
+    acc = torch.zeros(2, L, 4, 4, 4)
+    for wd in windows_of_rank(windows, rank, world, True):
+        pred = fake_unet(lat[:, :, wd])                                   # [2, 4, F, h, w]
+        accumulate(acc, pred.permute(0, 2, 1, 3, 4), wd)                  # acc is [B, L, C, h, w]
+    dist.all_reduce(acc)
+    out = combine(acc, inv, 3.5)
+    if rank == 0:
+        out_q.put(out)
+    dist.destroy_process_group()
+
+
+def test_window_sharding_world2_gloo():
+    """N>1 path on CPU: 2 ranks each process their windows; one sum all-reduce per step reproduces the single-process
+    overlap-average + CFG result."""
+    import torch.multiprocessing as mp
+    from aniportrait_b200.pipelines.sharding import accumulate, combine, plan_windows
+    L, world, port = 40, 2, 29533
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, L, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    windows, inv = plan_windows(L, 25)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, L, 4, 4, generator=g)
+    acc = torch.zeros(2, L, 4, 4, 4)
+    for wd in windows:
+        x = lat[:, :, wd]
+        pred = torch.stack([torch.sin(x[0] * 1.3), torch.cos(x[0] * 0.7)]) + x.mean(dim=2, keepdim=True)
+        accumulate(acc, pred.permute(0, 2, 1, 3, 4), wd)
+    ref = combine(acc, inv, 3.5)
+    assert torch.allclose(got, ref, atol=1e-5)
