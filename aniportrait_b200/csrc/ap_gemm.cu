@@ -5,7 +5,8 @@
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier full/empty)
 //   warp 1      MMA issuer    (tcgen05.mma cta_group::1, M=128, N=BN, K=16; accumulators double-buffered in TMEM)
-//   warps 2..5  epilogue      (tcgen05.ld -> +bias, +residual | GEGLU -> fp16 -> global), overlaps next tile's mainloop
+//   warps 2..9  epilogue      (tcgen05.ld -> +bias, +residual | GEGLU -> fp16 -> global), overlaps next tile's mainloop;
+//               two warps per TMEM lane quarter, each taking every other 32-column chunk
 //
 // The A operand is fetched by TMA in one of three addressing modes, so that linear layers, 1x1 convs, 3x3 convs
 // (stride 1 and 2, zero padding via TMA out-of-bounds fill) and channel-concatenated inputs (two K sources) share
@@ -64,10 +65,24 @@ struct GemmCfg {
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU, erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below fp16 output resolution):
+// 2 MUFU (rcp, ex2) + ~10 FMA instead of the ~30-instruction libdevice erff.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -96,7 +111,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     fence_mbar_init();
   }
@@ -183,6 +198,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are accessible to this warp
+    const int col_half = (warp - 2) >> 2;  // the two warps of a lane quarter take alternating 32-column chunks
     const int row = lane_group * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -214,11 +230,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(lane_group * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = col_half; c < BN / 32; c += 2) {
+        const int ncol = n_tile * BN + c * 32;  // column in weight-row space
+        // issue the residual loads first so that their latency overlaps the TMEM load
+        uint4 res4[4];
+        const bool vec_ok = (ncol + 32 <= p.n_valid) && ((p.ldo & 7) == 0);
+        const bool res_vec = EPI == EPI_LINEAR && p.residual != nullptr && row_ok && vec_ok && (p.ldr & 7) == 0;
+        if (res_vec) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + ncol);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) res4[q] = __ldg(r4 + q);
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
         tmem_ld_wait();
-        const int ncol = n_tile * BN + c * 32;  // column in weight-row space
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -254,15 +279,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           }
         } else {
           if (row_ok) {
-            const bool vec_ok = (ncol + 32 <= p.n_valid) && ((p.ldo & 7) == 0);
             if (p.residual != nullptr) {
-              const __half* rs = p.residual + m * p.ldr + ncol;
-              if (vec_ok && (p.ldr & 7) == 0) {
-                const uint4* r4 = reinterpret_cast<const uint4*>(rs);
+              if (res_vec) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  uint4 u = __ldg(r4 + q);
-                  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&res4[q]);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float2 f = __half22float2(h2[j]);
@@ -271,6 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                   }
                 }
               } else {
+                const __half* rs = p.residual + m * p.ldr + ncol;
                 for (int j = 0; j < 32; ++j)
                   if (ncol + j < p.n_valid) v[j] += __half2float(rs[j]);
               }
@@ -326,19 +348,29 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, p);
+  gemm_kernel<BN, EPI><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
 
-static int pick_bn(int N, int forced) {
+// Tile-width choice: wider tiles re-use the A operand more (less L2 traffic per FLOP) but give fewer tiles; small-M
+// problems (16x16 / 8x8 levels) prefer narrower tiles to fill the 148 SMs and reduce wave-quantisation loss.
+static int pick_bn(int N, int forced, long long m_tiles) {
   if (forced > 0) return forced;
-  if (N % 256 == 0) return 256;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  if (N % 64 == 0) return 64;
-  if (N % 32 == 0) return 32;
-  return -1;
+  const int cand[5] = {256, 160, 128, 64, 32};
+  const double quality[5] = {1.00, 0.95, 0.90, 0.70, 0.45};
+  int best = -1;
+  double best_score = -1.0;
+  const int sms = num_sms();
+  for (int i = 0; i < 5; ++i) {
+    if (N % cand[i] != 0) continue;
+    const long long tiles = m_tiles * (N / cand[i]);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double fill = (double)tiles / (double)(waves * sms);
+    const double score = fill * quality[i];
+    if (score > best_score + 1e-9) { best_score = score; best = cand[i]; }
+  }
+  return best;
 }
 
 static int dispatch(int bn, int epi, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
@@ -379,7 +411,7 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
   AP_REQUIRE(K1 % 64 == 0 || (a2 == nullptr), "gemm: K1 must be a multiple of 64 when a second source follows");
   AP_REQUIRE((lda % 8) == 0 && (a2 == nullptr || (lda2 % 8) == 0), "gemm: lda must be a multiple of 8 elements");
   const int epi = (flags & AP_GEMM_GEGLU) ? EPI_GEGLU : EPI_LINEAR;
-  const int bn = pick_bn(N, block_n);
+  const int bn = pick_bn(N, block_n, (M + 127) / 128);
   AP_REQUIRE(bn > 0 && N % bn == 0, "gemm: N=%d not tileable (block_n=%d)", N, block_n);
   const long long K = (long long)K1 + (a2 ? K2 : 0);
   AP_REQUIRE((K * 2) % 16 == 0, "gemm: K*2 bytes must be a multiple of 16");
@@ -437,7 +469,7 @@ extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2
   AP_REQUIRE(C1 % 64 == 0 && (x2 == nullptr || C2 % 64 == 0), "conv3x3: channels must be multiples of 64 (pad)");
   AP_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "conv3x3: stride 2 needs even H, W");
   const int Ho = H / stride, Wo = W / stride;
-  const int bn_ = pick_bn(Cout, block_n);
+  const int bn_ = pick_bn(Cout, block_n, ((long long)Nf * Ho * Wo + 127) / 128);
   AP_REQUIRE(bn_ > 0 && Cout % bn_ == 0, "conv3x3: Cout=%d not tileable", Cout);
 
   // tile box: bw x bh x bn output pixels = 128 rows, bw | Wo, bh | Ho (powers of two)

@@ -138,6 +138,19 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A (M x K fp16, K-major) is read from tensor memory: lane = row, every 32-bit
+// column holds two consecutive K elements (cute SM100_MMA_F16BF16_TS).
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed
 // (implicitly fences before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
