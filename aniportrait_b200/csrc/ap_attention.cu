@@ -45,6 +45,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// exp2 on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error ~1e-4, i.e. below the
+// fp16 rounding applied to P right after). The MUFU pipe issues only a few ex2 per clock per SM, which makes
+// 128x128x(d=40) attention tiles exp-bound; evaluating a fixed fraction of the exponentials this way (FlashAttention-4's
+// trick) balances the two pipes.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float magic = 12582912.0f;                 // 1.5 * 2^23: x + magic rounds x to the nearest integer
+  const float xr = x + magic;
+  const float f = x - (xr - magic);                // f in [-0.5, 0.5]
+  float pfrac = fmaf(0.05515501f, f, 0.24262067f);   // degree-3 minimax of 2^f on [-0.5, 0.5]: max rel err 7.6e-5
+  pfrac = fmaf(pfrac, f, 0.69325914f);
+  pfrac = fmaf(pfrac, f, 0.99992645f);
+  return __int_as_float(__float_as_int(pfrac) + (__float_as_int(xr) << 23));
+}
+
 struct AttnParams {
   int n_frames, tokens, heads, head_dim;
   int bank_tokens;        // 0 = no bank
@@ -702,7 +717,7 @@ struct Attn3Cfg {
   static_assert(DPAD % 64 == 0 && DPAD <= 128 && (BN == 64 || BN == 128), "tile config");
 };
 
-template <int DPAD, int BN>
+template <int DPAD, int BN, int EMU_NUM, int EMU_DEN>
 __global__ void __launch_bounds__(320, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
@@ -918,8 +933,12 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < BN; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
+          // every EMU_PERIOD-th pair goes to the FMA-pipe polynomial, the rest to MUFU.EX2
+          const bool emu = (EMU_NUM > 0) && (((i >> 1) % EMU_DEN) < EMU_NUM);
+          const float a0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run);
+          const float a1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run);
+          const float p0 = emu ? poly_exp2(a0) : fast_exp2(a0);
+          const float p1 = emu ? poly_exp2(a1) : fast_exp2(a1);
           ls[(i >> 1) & 3] += p0 + p1;
           const __half2 h = __floats2half2_rn(p0, p1);
           pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
@@ -973,18 +992,19 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int DPAD, int BN>
+template <int DPAD, int BN, int EMU_NUM, int EMU_DEN>
 static int launch_attention3(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = Attn3Cfg<DPAD, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(attention3_kernel<DPAD, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(attention3_kernel<DPAD, BN, EMU_NUM, EMU_DEN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int units = p.n_frames * p.heads * ((p.tokens + 255) / 256);
   const int grid = units < num_sms() ? units : num_sms();
-  attention3_kernel<DPAD, BN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  attention3_kernel<DPAD, BN, EMU_NUM, EMU_DEN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
+                                                                                         maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -1085,7 +1105,20 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
     maps[4] = maps[2];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_v3) return dpad == 64 ? launch_attention3<64, 128>(maps, p, st) : launch_attention3<128, 128>(maps, p, st);
+  if (use_v3) {
+    // fraction of exponentials evaluated on the FMA pipe: d=40 tiles are exp-bound (half), d=80 less so (quarter).
+    // AP_ATTENTION_EMU=0|1|2 overrides (0 = none, 1 = 1/4, 2 = 1/2) for A/B timing.
+    static const int emu_env = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : -1;
+    const int emu = emu_env >= 0 ? emu_env : (dpad == 64 ? 2 : 1);
+    if (dpad == 64) {
+      if (emu == 0) return launch_attention3<64, 128, 0, 4>(maps, p, st);
+      if (emu == 1) return launch_attention3<64, 128, 1, 4>(maps, p, st);
+      return launch_attention3<64, 128, 2, 4>(maps, p, st);
+    }
+    if (emu == 0) return launch_attention3<128, 128, 0, 4>(maps, p, st);
+    if (emu == 1) return launch_attention3<128, 128, 1, 4>(maps, p, st);
+    return launch_attention3<128, 128, 2, 4>(maps, p, st);
+  }
   if (use_v2) return dpad == 64 ? launch_attention2<64, 128>(maps, p, st) : launch_attention2<128, 64>(maps, p, st);
   if (dpad == 64) return launch_attention<64, 128>(maps, p, st);
   if (dpad == 128) return launch_attention<128, 128>(maps, p, st);

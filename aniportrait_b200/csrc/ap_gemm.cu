@@ -69,16 +69,16 @@ struct GemmCfg {
 // 2 MUFU (rcp, ex2) + ~10 FMA instead of the ~30-instruction libdevice erff.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2)
+  return fmaf(0.5f * fabsf(x), erf_abs, 0.5f * x);     // 0.5 x (1 + sign(x) erf_abs)
 }
 
 template <int BN, int EPI>

@@ -11,11 +11,12 @@ namespace ap {
 // Block = 8 warps = 8 heads of a group of positions (so whole 3C-wide token rows are consumed by one block);
 // lane = (position sub-index, query frame i). K then V are staged through shared memory in channel chunks.
 // ---------------------------------------------------------------------------------------------------------
-template <int FP>  // frames padded to a power of two: 4, 8, 16, 32
+template <int FP, int VEC>  // FP: frames padded to a power of two (4, 8, 16, 32); VEC: uint4 (8 halves) per channel chunk
 __global__ void __launch_bounds__(256)
 temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int B,
-                     int F, int N, int C, int heads, int CH, float scale) {
+                     int F, int N, int C, int heads, float scale) {
   constexpr int PW = 32 / FP;  // positions per warp
+  constexpr int CH = 8 * VEC;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int d = C / heads;
@@ -28,35 +29,43 @@ temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __res
   const int p = (int)(pos_group % groups_per_b) * PW + sub;
   const bool active = (i < F) && (p < N) && (warp < heads);
   extern __shared__ __align__(16) uint8_t tsm[];
-  // per warp: PW * FP rows x CH halves
-  __half* stage = reinterpret_cast<__half*>(tsm) + (size_t)warp * PW * FP * CH;
+  // per warp: K and V staging, PW * FP rows x CH halves each
+  __half* kst = reinterpret_cast<__half*>(tsm) + (size_t)warp * 2 * PW * FP * CH;
+  __half* vst = kst + PW * FP * CH;
   const long long row = ((long long)(b * F + (i < F ? i : 0))) * N + (p < N ? p : 0);
   const __half* qrow = qkv + row * ld + head * d;
   const __half* krow = qrow + C;
   const __half* vrow = qrow + 2 * C;
+  __half* orow = out + row * ldo + head * d;
+  const int chunks = d / CH;
+
+  // Pass 1: S = Q.K^T accumulated over channel chunks. All global loads of a chunk are issued before any is consumed.
   float s[FP];
 #pragma unroll
   for (int j = 0; j < FP; ++j) s[j] = 0.f;
-  const int vec = CH / 8;
-  for (int c0 = 0; c0 < d; c0 += CH) {
-    // stage this lane's K row chunk
+  for (int c = 0; c < chunks; ++c) {
+    uint4 qv[VEC], kv[VEC];
     if (active) {
-      for (int u = 0; u < vec; ++u)
-        *reinterpret_cast<uint4*>(stage + (sub * FP + i) * CH + u * 8) =
-            __ldg(reinterpret_cast<const uint4*>(krow + c0 + u * 8));
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        qv[u] = __ldg(reinterpret_cast<const uint4*>(qrow + c * CH + u * 8));
+        kv[u] = __ldg(reinterpret_cast<const uint4*>(krow + c * CH + u * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) *reinterpret_cast<uint4*>(kst + (sub * FP + i) * CH + u * 8) = kv[u];
     }
     __syncwarp();
     if (active) {
-      for (int u = 0; u < vec; ++u) {
-        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(qrow + c0 + u * 8));
-        const __half2* q2 = reinterpret_cast<const __half2*>(&qu);
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qv[u]);
         float2 qf[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) qf[t] = __half22float2(q2[t]);
 #pragma unroll
         for (int j = 0; j < FP; ++j) {
           if (j < F) {
-            const uint4 ku = *reinterpret_cast<const uint4*>(stage + (sub * FP + j) * CH + u * 8);
+            const uint4 ku = *reinterpret_cast<const uint4*>(kst + (sub * FP + j) * CH + u * 8);
             const __half2* k2 = reinterpret_cast<const __half2*>(&ku);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -81,23 +90,35 @@ temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __res
     l += s[j];
   }
   const float inv_l = 1.f / l;
-  __half* orow = out + row * ldo + head * d;
-  for (int c0 = 0; c0 < d; c0 += CH) {
+#pragma unroll
+  for (int j = 0; j < FP; ++j) s[j] *= inv_l;
+
+  // Pass 2: O = P.V per channel chunk (next chunk's V is in flight while this one is consumed).
+  uint4 vv[VEC];
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) vv[u] = __ldg(reinterpret_cast<const uint4*>(vrow + u * 8));
+  }
+  for (int c = 0; c < chunks; ++c) {
     if (active) {
-      for (int u = 0; u < vec; ++u)
-        *reinterpret_cast<uint4*>(stage + (sub * FP + i) * CH + u * 8) =
-            __ldg(reinterpret_cast<const uint4*>(vrow + c0 + u * 8));
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) *reinterpret_cast<uint4*>(vst + (sub * FP + i) * CH + u * 8) = vv[u];
+      if (c + 1 < chunks) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) vv[u] = __ldg(reinterpret_cast<const uint4*>(vrow + (c + 1) * CH + u * 8));
+      }
     }
     __syncwarp();
     if (active) {
-      for (int u = 0; u < vec; ++u) {
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
         float acc[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) acc[t] = 0.f;
 #pragma unroll
         for (int j = 0; j < FP; ++j) {
           if (j < F) {
-            const uint4 vu = *reinterpret_cast<const uint4*>(stage + (sub * FP + j) * CH + u * 8);
+            const uint4 vu = *reinterpret_cast<const uint4*>(vst + (sub * FP + j) * CH + u * 8);
             const __half2* v2 = reinterpret_cast<const __half2*>(&vu);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -109,8 +130,8 @@ temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __res
         }
         __half2 o[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv_l, acc[2 * t + 1] * inv_l);
-        *reinterpret_cast<uint4*>(orow + c0 + u * 8) = *reinterpret_cast<uint4*>(o);
+        for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t], acc[2 * t + 1]);
+        *reinterpret_cast<uint4*>(orow + c * CH + u * 8) = *reinterpret_cast<uint4*>(o);
       }
     }
     __syncwarp();
@@ -306,20 +327,28 @@ extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* ou
   AP_REQUIRE(heads >= 1 && heads <= 8 && C % heads == 0, "temporal_attention: heads=%d unsupported", heads);
   const int d = C / heads;
   AP_REQUIRE(d % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "temporal_attention: head_dim/ld must be multiples of 8");
-  int CH = 8;
-  for (int c : {40, 32, 16, 8})
-    if (d % c == 0) { CH = c; break; }
+  int VEC = 1;
+  for (int v : {5, 4, 2, 1})
+    if (d % (8 * v) == 0) { VEC = v; break; }
   const int FP = F <= 4 ? 4 : (F <= 8 ? 8 : (F <= 16 ? 16 : 32));
   const int PW = 32 / FP;
   const long long groups = (long long)B * ((N + PW - 1) / PW);
-  const size_t smem = (size_t)8 * PW * FP * CH * sizeof(__half);
-#define AP_T(FP_)                                                                                              \
-  temporal_attn_kernel<FP_><<<(unsigned)groups, 256, smem, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, B, F, \
-                                                                     N, C, heads, CH, scale)
-  if (FP == 4) AP_T(4);
-  else if (FP == 8) AP_T(8);
-  else if (FP == 16) AP_T(16);
-  else AP_T(32);
+  const size_t smem = (size_t)8 * 2 * PW * FP * (8 * VEC) * sizeof(__half);
+#define AP_T(FP_, V_)                                                                                             \
+  temporal_attn_kernel<FP_, V_><<<(unsigned)groups, 256, smem, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, B, \
+                                                                         F, N, C, heads, scale)
+#define AP_TV(FP_)                      \
+  do {                                  \
+    if (VEC == 5) AP_T(FP_, 5);         \
+    else if (VEC == 4) AP_T(FP_, 4);    \
+    else if (VEC == 2) AP_T(FP_, 2);    \
+    else AP_T(FP_, 1);                  \
+  } while (0)
+  if (FP == 4) AP_TV(4);
+  else if (FP == 8) AP_TV(8);
+  else if (FP == 16) AP_TV(16);
+  else AP_TV(32);
+#undef AP_TV
 #undef AP_T
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
