@@ -37,7 +37,7 @@ static int resolve_driver() {
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, bool swizzle128, int elem_bytes) {
+                const uint32_t* box, bool swizzle128, int elem_bytes, int swizzle_bytes) {
   int rc = resolve_driver();
   if (rc) return rc;
   cuuint64_t gdims[5];
@@ -59,7 +59,8 @@ int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* di
                                                               : CU_TENSOR_MAP_DATA_TYPE_UINT8);
   CUresult r = g_encode(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                            : (swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(AP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]",

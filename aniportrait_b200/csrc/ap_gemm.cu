@@ -19,6 +19,7 @@
 // nn.Linear / 1x1 nn.Conv2d in Transformer3DModel (src/models/transformer_3d.py:64-66,93-95), diffusers Attention
 // to_q/k/v/out and FeedForward(GEGLU) (src/models/attention.py:323-361, src/models/motion_module.py:122,144,233).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ap_host.h"
 #include "ap_ptx.cuh"
@@ -47,6 +48,9 @@ struct GemmParams {
   int ldo;
   int n_valid;             // columns >= n_valid are not stored
   int out_f32;             // store fp32 instead of fp16 (small bias-table GEMMs)
+  // TMA epilogue (per-warp 32-row x 32-column boxes staged in 64B-swizzled shared memory)
+  int tma_epi;             // 1: outputs leave through TMA stores, the residual arrives through TMA loads
+  int sub_w, sub_h, sub_n; // conv modes: geometry of a warp's 32-row sub-box
 };
 
 template <int BN>
@@ -56,11 +60,12 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int MAX_SMEM = 227 * 1024 - 2048;
+  static constexpr int EPI_STAGING = 8 * 4096;  // 8 epilogue warps x (2 KB output box + 2 KB residual box)
+  static constexpr int MAX_SMEM = 227 * 1024 - 2048 - EPI_STAGING;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment");
 };
@@ -84,18 +89,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+            const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;   // 1024-aligned: per warp [2 KB out | 2 KB residual]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_STAGING);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;   // [8] one per epilogue warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,6 +120,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 8);
+    }
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&tmOut);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmRes);
     }
     fence_mbar_init();
   }
@@ -202,6 +215,146 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     const int row = lane_group * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.tma_epi) {
+      // ---------------------------------------------------------------- TMA epilogue
+      // Each warp owns rows [32*lane_group, +32) of the tile and every other 32-output-column chunk. A chunk travels
+      // TMEM -> registers -> (bias / residual / GEGLU) -> fp16 -> this warp's 2 KB shared box (64B swizzle: bank-conflict
+      // free row-per-thread writes) -> one TMA store; the residual chunk arrives the same way through a TMA load that
+      // is issued one chunk ahead. No per-thread global memory instructions: row-per-thread LDG/STG touched 32
+      // different cache lines per instruction and made the small-K GEMMs L1-wavefront bound.
+      constexpr int ACC_PER_CHUNK = (EPI == EPI_GEGLU) ? 64 : 32;
+      constexpr int NCHUNK = BN / ACC_PER_CHUNK;
+      const int ew = warp - 2;
+      uint8_t* obuf = smem_epi + ew * 4096;
+      uint8_t* rbuf = obuf + 2048;
+      uint64_t* rbar = &res_bar[ew];
+      uint32_t rphase = 0;
+      const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
+      const int sw = (lane >> 1) & 3;                       // 64B-swizzle XOR term of this thread's row
+      const int r0 = lane_group * 32;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile % p.num_n_tiles;
+        // coordinates of this warp's 32-row box
+        int cy = 0, cx = 0, cn = 0;
+        long long m = 0;
+        bool row_ok = true;
+        if (p.a_mode == A_GEMM) {
+          cy = m_tile * Cfg::BM + r0;
+          m = (long long)cy + lane;
+          row_ok = m < p.M;
+        } else {
+          const int per_frame = p.tiles_x * p.tiles_y;
+          const int tn = m_tile / per_frame;
+          const int rem = m_tile % per_frame;
+          cn = tn * p.bn + r0 / (p.bh * p.bw);
+          cy = (rem / p.tiles_x) * p.bh + (r0 / p.bw) % p.bh;
+          cx = (rem % p.tiles_x) * p.bw + r0 % p.bw;
+          const int n = tn * p.bn + row / (p.bh * p.bw);
+          const int y = (rem / p.tiles_x) * p.bh + (row / p.bw) % p.bh;
+          const int x = (rem % p.tiles_x) * p.bw + row % p.bw;
+          row_ok = (n < p.Nf) && (y < p.Ho) && (x < p.Wo);
+          m = ((long long)n * p.Ho + y) * p.Wo + x;
+        }
+        const float* bias_row = nullptr;
+        if (p.bias != nullptr) bias_row = p.bias + (row_ok ? (m / p.bias_group_rows) : 0) * (long long)p.N;
+        auto load_res = [&](int chunk) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(rbar, 2048);
+            const int col = n_tile * BN + chunk * 32;
+            if (p.a_mode == A_GEMM) tma_load_2d(&tmRes, rbar, rbuf, col, cy);
+            else tma_load_4d(&tmRes, rbar, rbuf, col, cx, cy, cn);
+          }
+        };
+        if (has_res && col_half < NCHUNK) load_res(col_half);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(r0) << 16);
+#pragma unroll 1
+        for (int c = col_half; c < NCHUNK; c += 2) {
+          const int acol = n_tile * BN + c * ACC_PER_CHUNK;       // first accumulator (weight-row) column
+          float v[32];
+          if (EPI == EPI_GEGLU) {
+            uint32_t r[64];
+            tmem_ld_32x32b_x32(t_row + c * 64, r);
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, r + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float bv[16], bg[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { bv[j] = 0.f; bg[j] = 0.f; }
+              if (bias_row != nullptr) {
+                const float4* b4 = reinterpret_cast<const float4*>(bias_row + acol + h * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 a = __ldg(b4 + j), g = __ldg(b4 + 4 + j);
+                  bv[4 * j] = a.x; bv[4 * j + 1] = a.y; bv[4 * j + 2] = a.z; bv[4 * j + 3] = a.w;
+                  bg[4 * j] = g.x; bg[4 * j + 1] = g.y; bg[4 * j + 2] = g.z; bg[4 * j + 3] = g.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                v[h * 16 + j] = (__uint_as_float(r[h * 32 + j]) + bv[j]) *
+                                gelu_erf(__uint_as_float(r[h * 32 + 16 + j]) + bg[j]);
+            }
+          } else {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (bias_row != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_row + acol);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+            if (has_res) {
+              mbar_wait(rbar, rphase);
+              rphase ^= 1;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rbuf + lane * 64 + ((q ^ sw) << 4));
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(h2[j]);
+                  v[q * 8 + 2 * j] += f.x;
+                  v[q * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            }
+          }
+          // the previous TMA store out of obuf must have finished reading it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+            *reinterpret_cast<uint4*>(obuf + lane * 64 + ((q ^ sw) << 4)) = *reinterpret_cast<uint4*>(o);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (has_res && c + 2 < NCHUNK) load_res(c + 2);      // rbuf fully consumed by every lane (syncwarp above)
+          if (lane == 0) {
+            const int ocol = n_tile * (BN / (EPI == EPI_GEGLU ? 2 : 1)) + c * 32;
+            if (p.a_mode == A_GEMM) tma_store_2d(&tmOut, obuf, ocol, cy);
+            else tma_store_4d(&tmOut, obuf, ocol, cx, cy, cn);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all<0>();   // stores must complete before the CTA (and its smem) goes away
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile % p.num_n_tiles;
@@ -337,8 +490,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 // host side
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& to,
+                       const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -348,14 +501,14 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, p);
+  gemm_kernel<BN, EPI><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, to, tr, p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
 
 // Tile-width choice: wider tiles re-use the A operand more (less L2 traffic per FLOP) but give fewer tiles; small-M
 // problems (16x16 / 8x8 levels) prefer narrower tiles to fill the 148 SMs and reduce wave-quantisation loss.
-static int pick_bn(int N, int forced, long long m_tiles) {
+static int pick_bn(int N, int forced, long long m_tiles, bool geglu = false) {
   if (forced > 0) return forced;
   const int cand[5] = {256, 160, 128, 64, 32};
   const double quality[5] = {1.00, 0.95, 0.90, 0.70, 0.45};
@@ -364,6 +517,7 @@ static int pick_bn(int N, int forced, long long m_tiles) {
   const int sms = num_sms();
   for (int i = 0; i < 5; ++i) {
     if (N % cand[i] != 0) continue;
+    if (geglu && cand[i] % 64 != 0) continue;   // a GEGLU output chunk needs 64 accumulator columns
     const long long tiles = m_tiles * (N / cand[i]);
     const long long waves = (tiles + sms - 1) / sms;
     const double fill = (double)tiles / (double)(waves * sms);
@@ -374,11 +528,11 @@ static int pick_bn(int N, int forced, long long m_tiles) {
 }
 
 static int dispatch(int bn, int epi, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
-                    const GemmParams& p, cudaStream_t stream) {
-#define AP_CASE(BN_)                                                          \
-  case BN_:                                                                   \
-    return epi == EPI_GEGLU ? launch_gemm<BN_, EPI_GEGLU>(a1, a2, b, p, stream) \
-                            : launch_gemm<BN_, EPI_LINEAR>(a1, a2, b, p, stream);
+                    const CUtensorMap& to, const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
+#define AP_CASE(BN_)                                                                  \
+  case BN_:                                                                           \
+    return epi == EPI_GEGLU ? launch_gemm<BN_, EPI_GEGLU>(a1, a2, b, to, tr, p, stream) \
+                            : launch_gemm<BN_, EPI_LINEAR>(a1, a2, b, to, tr, p, stream);
   switch (bn) {
     AP_CASE(256)
     AP_CASE(160)
@@ -411,7 +565,8 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
   AP_REQUIRE(K1 % 64 == 0 || (a2 == nullptr), "gemm: K1 must be a multiple of 64 when a second source follows");
   AP_REQUIRE((lda % 8) == 0 && (a2 == nullptr || (lda2 % 8) == 0), "gemm: lda must be a multiple of 8 elements");
   const int epi = (flags & AP_GEMM_GEGLU) ? EPI_GEGLU : EPI_LINEAR;
-  const int bn = pick_bn(N, block_n, (M + 127) / 128);
+  const int bn = pick_bn(N, block_n, (M + 127) / 128, epi == EPI_GEGLU);
+  AP_REQUIRE(epi != EPI_GEGLU || (bn > 0 && bn % 64 == 0), "gemm: GEGLU needs a BLOCK_N multiple of 64");
   AP_REQUIRE(bn > 0 && N % bn == 0, "gemm: N=%d not tileable (block_n=%d)", N, block_n);
   const long long K = (long long)K1 + (a2 ? K2 : 0);
   AP_REQUIRE((K * 2) % 16 == 0, "gemm: K*2 bytes must be a multiple of 16");
@@ -456,7 +611,23 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
   }
   int rc = make_weight_map(&tmB, w, N, K, bn);
   if (rc) return rc;
-  return dispatch(bn, epi, tmA1, tmA2, tmB, p, (cudaStream_t)stream);
+  // TMA epilogue whenever the output (and residual) satisfy TMA's 16-byte rules
+  CUtensorMap tmOut = tmB, tmRes = tmB;
+  const bool aligned_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 8) == 0 && (p.n_valid % 8) == 0;
+  const bool aligned_res = residual == nullptr || ((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (ldr % 8) == 0);
+  static const bool no_tma_epi = getenv("AP_GEMM_NO_TMA_EPI") != nullptr;
+  if (!p.out_f32 && aligned_out && aligned_res && !no_tma_epi) {
+    const uint64_t dims[2] = {(uint64_t)p.n_valid, (uint64_t)M};
+    const uint32_t box[2] = {32, 32};
+    const uint64_t so[1] = {(uint64_t)ldo * 2};
+    if ((rc = encode_tmap(&tmOut, out, 2, dims, so, box, false, 2, 64))) return rc;
+    if (residual) {
+      const uint64_t sr[1] = {(uint64_t)ldr * 2};
+      if ((rc = encode_tmap(&tmRes, residual, 2, dims, sr, box, false, 2, 64))) return rc;
+    }
+    p.tma_epi = 1;
+  }
+  return dispatch(bn, epi, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }
 
 // 3x3 convolution, padding 1, stride 1 or 2, NHWC fp16, optional channel-concatenated second input.
@@ -526,5 +697,20 @@ extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2
   }
   rc = make_weight_map(&tmB, w, Cout, 9ll * (C1 + (x2 ? C2 : 0)), bn_);
   if (rc) return rc;
-  return dispatch(bn_, EPI_LINEAR, tmA1, tmA2, tmB, p, (cudaStream_t)stream);
+  CUtensorMap tmOut = tmB, tmRes = tmB;
+  const bool aligned_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 8) == 0 && (p.n_valid % 8) == 0;
+  const bool aligned_res = residual == nullptr || (reinterpret_cast<uintptr_t>(residual) & 15) == 0;
+  static const bool no_tma_epi = getenv("AP_GEMM_NO_TMA_EPI") != nullptr;
+  if (aligned_out && aligned_res && !no_tma_epi) {
+    p.sub_w = bw < 32 ? bw : 32;
+    p.sub_h = bh < 32 / p.sub_w ? bh : 32 / p.sub_w;
+    p.sub_n = 32 / (p.sub_w * p.sub_h);
+    const uint64_t dims[4] = {(uint64_t)p.n_valid, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)Nf};
+    const uint64_t so[3] = {(uint64_t)ldo * 2, (uint64_t)Wo * ldo * 2, (uint64_t)Ho * Wo * ldo * 2};
+    const uint32_t box[4] = {32, (uint32_t)p.sub_w, (uint32_t)p.sub_h, (uint32_t)p.sub_n};
+    if ((rc = encode_tmap(&tmOut, out, 4, dims, so, box, false, 2, 64))) return rc;
+    if (residual && (rc = encode_tmap(&tmRes, residual, 4, dims, so, box, false, 2, 64))) return rc;
+    p.tma_epi = 1;
+  }
+  return dispatch(bn_, EPI_LINEAR, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }

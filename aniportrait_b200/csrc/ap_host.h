@@ -16,7 +16,7 @@ int fail(int code, const char* fmt, ...);
 // library also loads on a CPU-only box for symbol checks).
 // dims/box are innermost-first; strides_bytes has rank-1 entries (stride of dim 1..rank-1).
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, bool swizzle128, int elem_bytes = 2);
+                const uint32_t* box, bool swizzle128, int elem_bytes = 2, int swizzle_bytes = 0);
 
 int num_sms();
 
