@@ -179,6 +179,47 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long rows, i
   }
 }
 
+// Row softmax (fp16 in/out, fp32 math) for the VAE's single-head 4096-token attention, which is evaluated as
+// GEMM -> softmax -> GEMM (head dim 512 does not fit the fused attention kernel's TMEM budget). One block per row.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                           int cols, long long ld) {
+  const long long row = blockIdx.x;
+  const __half2* src = reinterpret_cast<const __half2*>(x + row * ld);
+  __half2* dst = reinterpret_cast<__half2*>(y + row * ld);
+  const int nv = cols >> 1;
+  __shared__ float red[8];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float2 f = __half22float2(src[i]);
+    mx = fmaxf(mx, fmaxf(f.x, f.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float2 f = __half22float2(src[i]);
+    sum += __expf(f.x - mx) + __expf(f.y - mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float2 f = __half22float2(src[i]);
+    dst[i] = __floats2half2_rn(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+  }
+}
+
 static void gn_launch_geometry(int HW, int C, int Nf, int* threads, int* rows_per_block, int* chunks) {
   const int vecs = C / 8;
   int k = 256 / vecs;
@@ -230,6 +271,13 @@ extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int 
                                                                        cpg, rpb, stats, groups, inv_count, eps, gamma,
                                                                        beta, (__half*)out);
   }
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_softmax_rows_f16(const void* x, void* out, long long rows, int cols, long long ld, void* stream) {
+  AP_REQUIRE(x && out && cols % 2 == 0 && ld % 2 == 0, "softmax_rows: cols/ld must be even");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, cols, ld);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }

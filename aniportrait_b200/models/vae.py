@@ -1,9 +1,11 @@
 """AutoencoderKL (sd-vae-ft-mse layout) with diffusers' parameter names so published checkpoints load.
 
 Role on the hot path: `decode` of the denoised latents (reference pipeline_pose2vid_long.py:113-126, one frame per
-call) and a single `encode` of the reference image. Round-1 status: both run as batched fp16 torch/cuDNN library ops
-(decode is batched over frames instead of frame-at-a-time); the sm_100a conv / GroupNorm kernels already cover every
-decoder layer shape and replacing this module's forward with them is the first "next" row.
+call) and a single `encode` of the reference image (once per video, :430-431).
+  * `decode` on a CUDA fp16 model runs on the sm_100a kernels (channels-last, batched over frames): implicit-GEMM 3x3
+    convs, fused GroupNorm+SiLU, tcgen05 GEMMs for the 1x1 shortcuts and the mid-block attention, which (single head,
+    d = 512: too wide for the fused attention kernel's TMEM budget) is evaluated per frame as GEMM -> row-softmax -> GEMM.
+  * `encode` (once per video, off the per-step path) and any non-fp16 / non-CUDA use run as torch library ops.
 """
 from __future__ import annotations
 
@@ -13,7 +15,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .modeling import ModelBase
+from .. import ops
+from .modeling import ModelBase, PackedCache, f16, f32
 
 
 class _Resnet(nn.Module):
@@ -131,6 +134,81 @@ class Decoder(nn.Module):
             x = b(x)
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
+    # ------------------------------------------------------------------------------------------ kernel path
+    def _packed(self):
+        if not hasattr(self, "_pk"):
+            self._pk = PackedCache()
+
+        def conv(c):
+            w = ops.pack_conv3x3_weight(c.weight.detach())
+            b = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+            b[:c.out_channels] = f32(c.bias)
+            return w, b
+
+        def res(r):
+            d = dict(g1=f32(r.norm1.weight), b1=f32(r.norm1.bias), g2=f32(r.norm2.weight), b2=f32(r.norm2.bias),
+                     c1=conv(r.conv1), c2=conv(r.conv2), cout=r.conv1.out_channels)
+            if r.conv_shortcut is not None:
+                d["ws"] = f16(r.conv_shortcut.weight.reshape(r.conv_shortcut.out_channels, -1))
+                d["bs"] = f32(r.conv_shortcut.bias)
+            return d
+
+        def build():
+            a = self.mid_block.attentions[0]
+            c = a.to_q.weight.shape[0]
+            scale = c ** -0.5
+            pk = dict(conv_in=conv(self.conv_in), mid=[res(r) for r in self.mid_block.resnets],
+                      attn=dict(g=f32(a.group_norm.weight), b=f32(a.group_norm.bias),
+                                # softmax scale folded into the q projection; v bias folded into the output bias
+                                # (softmax rows sum to 1): out = P.(xWv^T) Wo^T + (Wo bv + bo)
+                                wq=f16(a.to_q.weight * scale), bq=f32(a.to_q.bias * scale), wk=f16(a.to_k.weight),
+                                bk=f32(a.to_k.bias), wv=f16(a.to_v.weight), wo=f16(a.to_out[0].weight),
+                                bo=f32(a.to_out[0].bias) + f32(a.to_out[0].weight) @ f32(a.to_v.bias), c=c),
+                      up=[dict(res=[res(r) for r in b.resnets],
+                               up=conv(b.upsamplers[0].conv) if b._sampler == "up" else None) for b in self.up_blocks],
+                      gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)), conv_out=conv(self.conv_out))
+            return pk
+        return self._pk.get(self, build)
+
+    @staticmethod
+    def _res_run(x, d, groups):
+        nf, h, w, cin = x.shape
+        hn = ops.group_norm(x, d["g1"], d["b1"], groups, 1e-6, True)
+        hc = ops.conv3x3(hn, d["c1"][0], d["cout"], bias=d["c1"][1])
+        hn2 = ops.group_norm(hc, d["g2"], d["b2"], groups, 1e-6, True)
+        res = ops.gemm(x.view(-1, cin), d["ws"], bias=d["bs"]).view(nf, h, w, d["cout"]) if "ws" in d else x
+        return ops.conv3x3(hn2, d["c2"][0], d["cout"], bias=d["c2"][1], residual=res)
+
+    def run_nhwc(self, z: torch.Tensor, groups: int = 32) -> torch.Tensor:
+        """z: [Nf, h, w, 64] fp16 (4 latent channels zero padded) -> [Nf, 8h, 8w, 3] fp16."""
+        pk = self._packed()
+        x = ops.conv3x3(z, pk["conv_in"][0], self.conv_in.out_channels, bias=pk["conv_in"][1])
+        x = self._res_run(x, pk["mid"][0], groups)
+        # mid-block attention, one frame at a time (the [tokens, tokens] score matrix is 32 MB per frame at 512x512)
+        a = pk["attn"]
+        nf, h, w, c = x.shape
+        n = h * w
+        hn = ops.group_norm(x, a["g"], a["b"], groups, 1e-6, False).view(nf, n, c)
+        q = ops.gemm(hn.view(-1, c), a["wq"], bias=a["bq"]).view(nf, n, c)
+        k = ops.gemm(hn.view(-1, c), a["wk"], bias=a["bk"]).view(nf, n, c)
+        att = torch.empty(nf, n, c, dtype=torch.float16, device=x.device)
+        npad = (n + 31) // 32 * 32
+        for f in range(nf):
+            vt = ops.gemm(a["wv"], hn[f].contiguous())                   # V^T = Wv . X^T  [c, n]
+            sc = ops.gemm(q[f], k[f].contiguous() if npad == n else
+                          torch.cat([k[f], k[f].new_zeros(npad - n, c)]), n_valid=n)   # [n, n] scaled scores
+            ops.softmax_rows(sc)
+            ops.gemm(sc, vt, out=att[f])                                  # P . V   (K = n keys)
+        x = ops.gemm(att.view(-1, c), a["wo"], bias=a["bo"], residual=x.view(-1, c)).view(nf, h, w, c)
+        x = self._res_run(x, pk["mid"][1], groups)
+        for blk in pk["up"]:
+            for d in blk["res"]:
+                x = self._res_run(x, d, groups)
+            if blk["up"] is not None:
+                x = ops.conv3x3(ops.upsample2x(x), blk["up"][0], x.shape[-1], bias=blk["up"][1])
+        hn = ops.group_norm(x, pk["gn"][0], pk["gn"][1], groups, 1e-6, True)
+        return ops.conv3x3(hn, pk["conv_out"][0], self.conv_out.out_channels, bias=pk["conv_out"][1])
+
 
 class _LatentDist:
     def __init__(self, moments):
@@ -176,6 +254,21 @@ class AutoencoderKL(ModelBase):
     def encode(self, x, return_dict=True):
         return AutoencoderKLOutput(latent_dist=_LatentDist(self.quant_conv(self.encoder(x))))
 
+    def _kernel_decode_ok(self, z):
+        boc = self.config.block_out_channels
+        return (z.is_cuda and self.dtype == torch.float16 and all(c % 64 == 0 for c in boc)
+                and z.shape[-1] % 8 == 0 and z.shape[-2] % 8 == 0 and (z.shape[-1] * z.shape[-2]) % 64 == 0)
+
     @torch.no_grad()
     def decode(self, z, return_dict=True, generator=None):
-        return DecoderOutput(sample=self.decoder(self.post_quant_conv(z)))
+        """z [n, 4, h, w] -> sample [n, 3, 8h, 8w]. fp16 CUDA models with 64-multiple widths (sd-vae-ft-mse) take the
+        sm_100a kernel path; the 4->4 post_quant 1x1 conv is a per-pixel 4x4 matmul done while converting layouts."""
+        if not self._kernel_decode_ok(z):
+            return DecoderOutput(sample=self.decoder(self.post_quant_conv(z)))
+        n, c, h, w = z.shape
+        wq = self.post_quant_conv.weight.reshape(c, c).to(torch.float32)
+        zq = torch.einsum("nchw,oc->nhwo", z.to(torch.float32), wq) + self.post_quant_conv.bias.to(torch.float32)
+        zp = torch.zeros(n, h, w, 64, dtype=torch.float16, device=z.device)
+        zp[..., :c] = zq.to(torch.float16)
+        out = self.decoder.run_nhwc(zp, self.config.norm_num_groups)
+        return DecoderOutput(sample=out.permute(0, 3, 1, 2))

@@ -178,6 +178,16 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     return out
 
 
+def softmax_rows(x: torch.Tensor) -> torch.Tensor:
+    """In-place row softmax of an fp16 matrix [rows, cols] (cols even)."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.dim() == 2 and x.stride(1) == 1
+    check(lib().ap_softmax_rows_f16(ptr(x), ptr(x), LL(x.shape[0]), I(x.shape[1]), LL(x.stride(0)), stream_ptr()),
+          "ap_softmax_rows_f16")
+    _count()
+    return x
+
+
 # --------------------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------------------

@@ -81,6 +81,10 @@ int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf,
 int ap_layernorm_f16(const void* x, long long rows, int C, float eps, const float* gamma, const float* beta,
                      const float* pe, int rows_per_pe, int pe_period, void* out, void* stream);
 
+/* Row softmax, fp16 in/out (may be in place), fp32 math: the VAE mid-block attention (single head, d = 512) is evaluated as
+ * GEMM -> softmax -> GEMM (diffusers AutoencoderKL [dep], reference pipeline_pose2vid_long.py:118-121). */
+int ap_softmax_rows_f16(const void* x, void* out, long long rows, int cols, long long ld, void* stream);
+
 /*
  * Fused spatial self / reference attention (flash-style, tcgen05). q/k/v: [n_frames*tokens, ld_qkv] fp16 with head h
  * at columns [h*dpad, h*dpad + head_dim) (zero padded to dpad in {64,128,192}); frames >= first_bank_frame also attend
