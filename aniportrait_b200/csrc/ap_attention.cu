@@ -1056,8 +1056,10 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* v_full = k_full + ST;         // [ST]
   uint64_t* kv_empty = v_full + ST;       // [ST]
   uint64_t* s_full = kv_empty + ST;       // [4] per (query tile, S buffer)
-  uint64_t* p_full = s_full + 4;          // [2]
-  uint64_t* o_done = p_full + 2;          // [2]
+  uint64_t* p_full = s_full + 4;          // [4] per (query tile, S buffer): a softmax warpgroup may run up to two
+                                          // key tiles ahead of the MMA warp, so one barrier per buffer keeps every
+                                          // barrier at most one phase ahead of its waiter (parity waits alias otherwise)
+  uint64_t* o_done = p_full + 4;          // [2]
   uint64_t* pv_done = o_done + 2;         // [2] (only waited on by the rare O-rescale path)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
@@ -1078,7 +1080,8 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[2 * t], 1);
       mbar_init(&s_full[2 * t + 1], 1);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&p_full[2 * t], 4);
+      mbar_init(&p_full[2 * t + 1], 4);
       mbar_init(&o_done[t], 1);
       mbar_init(&pv_done[t], 1);
     }
@@ -1165,7 +1168,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       };
       auto issue_pv = [&](int t, uint32_t gi, int j, bool last) {
         const int stage = gi % ST;
-        mbar_wait(&p_full[t], gi & 1);
+        mbar_wait(&p_full[2 * t + (gi & 1)], (gi >> 1) & 1);
         mbar_wait(&v_full[stage], (gi / ST) & 1);
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + Cfg::TMEM_S + t * 128 + (gi & 1) * 64;   // P aliases its S buffer
@@ -1282,7 +1285,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive(&p_full[2 * t + (g & 1)]);
       }
       // ------------------------------------------------------------------ epilogue
       mbar_wait(&o_done[t], uc & 1);

@@ -65,7 +65,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > AP_MBAR_TIMEOUT_CYCLES) {
-      printf("ap: mbarrier timeout block=(%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+      printf("ap: mbarrier timeout block=(%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x, blockIdx.y, threadIdx.x,
+             smem_u32(bar), parity);
       __trap();
     }
   }
