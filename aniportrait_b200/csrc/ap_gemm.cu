@@ -53,12 +53,12 @@ struct GemmParams {
   int sub_w, sub_h, sub_n; // conv modes: geometry of a warp's 32-row sub-box
 };
 
-template <int BN>
+template <int BN, int CG = 1>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;   // cta_group::2: each CTA of the pair stages half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_STAGING = 8 * 4096;  // 8 epilogue warps x (2 KB output box + 2 KB residual box)
   static constexpr int MAX_SMEM = 227 * 1024 - 2048 - EPI_STAGING;
@@ -86,13 +86,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(0.5f * fabsf(x), erf_abs, 0.5f * x);     // 0.5 x (1 + sign(x) erf_abs)
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
             const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
+  // CG == 2: the CTAs of a pair (cluster of 2) work on two vertically adjacent 128-row tiles with ONE M=256 MMA issued
+  // by the leader (rank 0). `cta_rank` selects this CTA's A rows and its half of the B tile.
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -107,7 +110,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // work items: tiles (CG == 1) or pair-tiles of 2 x 128 rows (CG == 2); every CTA of a pair walks the same sequence
+  const int num_tiles = (p.num_m_tiles / CG) * p.num_n_tiles;
+  const int first_tile = blockIdx.x / CG;
+  const int tile_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -119,7 +125,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], 8 * CG);   // CG == 2: the leader's barrier collects both CTAs' epilogue warps
     }
     for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     if (p.tma_epi) {
@@ -128,7 +134,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (CG == 2) cluster_sync();   // barrier inits visible cluster-wide before any remote arrive / 2-SM TMA
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,8 +150,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       const int kb_per_tap = p.kb_src1 + p.kb_src2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
         const int n_tile = tile % p.num_n_tiles;
         int n0 = 0, y0 = 0, x0 = 0;
         if (p.a_mode != A_GEMM) {
@@ -154,7 +164,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          // CG == 2: only the leader arms its barrier, with the bytes of BOTH CTAs (their TMA loads signal it)
+          if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
           void* a_dst = smem_a + stage * Cfg::A_BYTES;
           void* b_dst = smem_b + stage * Cfg::B_BYTES;
           const int tap = kb / kb_per_tap;
@@ -163,31 +174,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           const CUtensorMap* am = second ? &tmA2 : &tmA1;
           const int c0 = (second ? within - p.kb_src1 : within) * Cfg::BK;
           if (p.a_mode == A_GEMM) {
-            tma_load_2d(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
+            if (CG == 2) tma_load_2d_2sm(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
+            else tma_load_2d(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
           } else if (p.a_mode == A_CONV_S1) {
             const int ky = tap / 3, kx = tap % 3;
-            tma_load_4d(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
+            if (CG == 2) tma_load_4d_2sm(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
+            else tma_load_4d(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
           } else {
             // input pixel = 2*o + k - 1  ->  k=0: (o-1, phase 1), k=1: (o, phase 0), k=2: (o, phase 1)
             const int ky = tap / 3, kx = tap % 3;
             const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
             const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
-            tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
+            if (CG == 2) tma_load_5d_2sm(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
+            else tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
           }
-          tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
+          if (CG == 2) tma_load_2d_2sm(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN + (int)cta_rank * (BN / 2));
+          else tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128 * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -199,10 +214,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in the (>>4) start-address field
-            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (CG == 2) {
+            umma_commit_2sm_mc(&empty_bar[stage], 3);                       // frees the stage in both CTAs
+            if (kb == p.num_kb - 1) umma_commit_2sm_mc(&tmem_full[acc], 3);  // wakes both CTAs' epilogues
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -232,8 +253,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
       const int sw = (lane >> 1) & 3;                       // 64B-swizzle XOR term of this thread's row
       const int r0 = lane_group * 32;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
         const int n_tile = tile % p.num_n_tiles;
         // coordinates of this warp's 32-row box
         int cy = 0, cx = 0, cn = 0;
@@ -350,13 +371,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) tma_store_wait_all<0>();   // stores must complete before the CTA (and its smem) goes away
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+      const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
       const int n_tile = tile % p.num_n_tiles;
       // output row of this thread
       long long m;
@@ -473,35 +497,57 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // no CTA of the pair may exit (or free TMEM) while its peer can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (CG == 2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& to,
                        const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, to, tr, p);
+  const int items = (p.num_m_tiles / CG) * p.num_n_tiles;
+  const int max_ctas = (num_sms() / CG) * CG;
+  const int grid = items * CG < max_ctas ? items * CG : max_ctas;
+  if (CG == 1) {
+    gemm_kernel<BN, EPI, CG><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, to, tr, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG>, a1, a2, b, to, tr, p));
+  }
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -527,12 +573,26 @@ static int pick_bn(int N, int forced, long long m_tiles, bool geglu = false) {
   return best;
 }
 
-static int dispatch(int bn, int epi, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
+static int dispatch(int bn, int epi, int cg, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
                     const CUtensorMap& to, const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
-#define AP_CASE(BN_)                                                                  \
-  case BN_:                                                                           \
-    return epi == EPI_GEGLU ? launch_gemm<BN_, EPI_GEGLU>(a1, a2, b, to, tr, p, stream) \
-                            : launch_gemm<BN_, EPI_LINEAR>(a1, a2, b, to, tr, p, stream);
+#define AP_CASE(BN_)                                                                     \
+  case BN_:                                                                              \
+    return epi == EPI_GEGLU ? launch_gemm<BN_, EPI_GEGLU, 1>(a1, a2, b, to, tr, p, stream) \
+                            : launch_gemm<BN_, EPI_LINEAR, 1>(a1, a2, b, to, tr, p, stream);
+#define AP_CASE2(BN_)                                                                    \
+  case BN_:                                                                              \
+    return epi == EPI_GEGLU ? launch_gemm<BN_, EPI_GEGLU, 2>(a1, a2, b, to, tr, p, stream) \
+                            : launch_gemm<BN_, EPI_LINEAR, 2>(a1, a2, b, to, tr, p, stream);
+  if (cg == 2) {
+    switch (bn) {
+      AP_CASE2(256)
+      case 160:
+        return launch_gemm<160, EPI_LINEAR, 2>(a1, a2, b, to, tr, p, stream);
+      AP_CASE2(128)
+      default:
+        return fail(AP_ERR_INVALID, "gemm: unsupported 2-CTA BLOCK_N %d", bn);
+    }
+  }
   switch (bn) {
     AP_CASE(256)
     AP_CASE(160)
@@ -543,12 +603,23 @@ static int dispatch(int bn, int epi, const CUtensorMap& a1, const CUtensorMap& a
       return fail(AP_ERR_INVALID, "gemm: unsupported BLOCK_N %d", bn);
   }
 #undef AP_CASE
+#undef AP_CASE2
 }
 
-static int make_weight_map(CUtensorMap* tm, const void* w, int N, long long K, int bn) {
+// cta_group::2 is used when the work splits into pairs of 128-row tiles and the tile is wide enough to profit
+static int pick_cg(int bn, int num_m_tiles, int num_n_tiles) {
+  static const int env = getenv("AP_GEMM_CG") ? atoi(getenv("AP_GEMM_CG")) : 0;
+  if (env == 1) return 1;
+  if (num_m_tiles % 2 != 0) return 1;
+  if (!(bn == 256 || bn == 160 || bn == 128)) return 1;
+  if ((long long)num_m_tiles * num_n_tiles < 2LL * 74 && env != 2) return 1;   // too few pair-tiles to fill the chip
+  return 2;
+}
+
+static int make_weight_map(CUtensorMap* tm, const void* w, int N, long long K, int bn_box) {
   const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t strides[1] = {(uint64_t)K * 2};
-  const uint32_t box[2] = {64, (uint32_t)bn};
+  const uint32_t box[2] = {64, (uint32_t)bn_box};
   return encode_tmap(tm, w, 2, dims, strides, box, true);
 }
 
@@ -609,7 +680,8 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
   } else {
     tmA2 = tmA1;
   }
-  int rc = make_weight_map(&tmB, w, N, K, bn);
+  const int cg = pick_cg(bn, p.num_m_tiles, p.num_n_tiles);
+  int rc = make_weight_map(&tmB, w, N, K, bn / cg);
   if (rc) return rc;
   // TMA epilogue whenever the output (and residual) satisfy TMA's 16-byte rules
   CUtensorMap tmOut = tmB, tmRes = tmB;
@@ -627,7 +699,7 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
     }
     p.tma_epi = 1;
   }
-  return dispatch(bn, epi, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
+  return dispatch(bn, epi, cg, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }
 
 // 3x3 convolution, padding 1, stride 1 or 2, NHWC fp16, optional channel-concatenated second input.
@@ -695,7 +767,8 @@ extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2
   } else {
     tmA2 = tmA1;
   }
-  rc = make_weight_map(&tmB, w, Cout, 9ll * (C1 + (x2 ? C2 : 0)), bn_);
+  const int cg = pick_cg(bn_, p.num_m_tiles, p.num_n_tiles);
+  rc = make_weight_map(&tmB, w, Cout, 9ll * (C1 + (x2 ? C2 : 0)), bn_ / cg);
   if (rc) return rc;
   CUtensorMap tmOut = tmB, tmRes = tmB;
   const bool aligned_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 8) == 0 && (p.n_valid % 8) == 0;
@@ -712,5 +785,5 @@ extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2
     if (residual && (rc = encode_tmap(&tmRes, residual, 4, dims, so, box, false, 2, 64))) return rc;
     p.tma_epi = 1;
   }
-  return dispatch(bn_, EPI_LINEAR, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
+  return dispatch(bn_, EPI_LINEAR, cg, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }
