@@ -818,8 +818,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tma_load_2d(mv, &v_full[stage], vd + s * (BN * 128), head * DPAD + s * 64, row);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------------ MMA issuer (warp-uniform loop, one
+      // elected lane issues: keeps descriptor / stage arithmetic in uniform registers)
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);
       uint32_t g = 0, uc = 0;
@@ -830,14 +831,17 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t d_tmem = tmem_base + Cfg::TMEM_S + t * 128;
         const uint32_t qa = smem_u32(smem_q + t * Cfg::QT_BYTES);
         const uint32_t ka = smem_u32(smem_kv + stage * Cfg::KV_STAGE);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DPAD / 16; ++kk) {
-          const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
-          const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
-          umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
+          for (int kk = 0; kk < DPAD / 16; ++kk) {
+            const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
+            const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
+            umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
+          }
+          umma_commit(&s_full[t]);
+          if (release_q) umma_commit(q_empty);
         }
-        umma_commit(&s_full[t]);
-        if (release_q) umma_commit(q_empty);
+        __syncwarp();
       };
       auto issue_pv = [&](int t, uint32_t gi, int j, bool last) {
         const int stage = gi % ST;
@@ -846,13 +850,16 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + Cfg::TMEM_S + t * 128;   // P aliases the first BN/2 columns of S
         const uint32_t va = smem_u32(smem_kv + stage * Cfg::KV_STAGE + Cfg::K_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t db = umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128);
-          umma_f16_ts(tmem_base + Cfg::TMEM_O + t * DPAD, a_tmem + kk * 8, db, idesc_pv, (j | kk) != 0);
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            const uint64_t db = umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128);
+            umma_f16_ts(tmem_base + Cfg::TMEM_O + t * DPAD, a_tmem + kk * 8, db, idesc_pv, (j | kk) != 0);
+          }
+          if (t == 1) umma_commit(&kv_empty[stage]);
+          if (last) umma_commit(&o_done[t]);
         }
-        if (t == 1) umma_commit(&kv_empty[stage]);
-        if (last) umma_commit(&o_done[t]);
+        __syncwarp();
       };
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
         int frame, head, m_pair, T;

@@ -196,12 +196,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp walks the loop with warp-uniform state (so ptxas keeps stage / descriptor math in uniform
+    // registers instead of per-instruction R2UR broadcast loops); one elected lane issues tcgen05.mma / commit.
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128 * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -209,21 +212,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+          const uint64_t da = umma_desc_k_sw128(a_base + stage * Cfg::A_BYTES);
+          const uint64_t db = umma_desc_k_sw128(b_base + stage * Cfg::B_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k) {
-            // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in the (>>4) start-address field
-            if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in the (>>4) start-address field
+              if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (CG == 2) {
+              umma_commit_2sm_mc(&empty_bar[stage], 3);                       // frees the stage in both CTAs
+              if (kb == p.num_kb - 1) umma_commit_2sm_mc(&tmem_full[acc], 3);  // wakes both CTAs' epilogues
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+            }
           }
-          if (CG == 2) {
-            umma_commit_2sm_mc(&empty_bar[stage], 3);                       // frees the stage in both CTAs
-            if (kb == p.num_kb - 1) umma_commit_2sm_mc(&tmem_full[acc], 3);  // wakes both CTAs' epilogues
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
-          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -231,6 +231,13 @@ class BasicTransformerBlock(nn.Module):
             self._bank_kv = (key, kv, nb)
         return self._bank_kv[1], self._bank_kv[2]
 
+    def prepare(self, ctx: RunCtx):
+        """Per-video precompute (outside any CUDA-graph capture): attn2 constant and the bank's K/V projection."""
+        pk = self.packed()
+        self._attn_out_bias(pk, ctx)
+        if self._ref_mode == "read" and len(self.bank) > 0:
+            self._bank_projection(pk, self.bank[0].shape[1])
+
     def run(self, t0: torch.Tensor, n_frames: int, tokens: int, ctx: RunCtx) -> torch.Tensor:
         """t0: [n_frames*tokens, dim] fp16."""
         pk = self.packed()

@@ -251,6 +251,17 @@ class UNet3DConditionModel(ModelBase):
         hn = ops.group_norm(x, pk["gn"], pk["bn"], self.groups, self.eps, True)
         return ops.conv3x3(hn, pk["wo"], self.conv_out.out_channels, bias=pk["bo"])
 
+    def prepare_reference(self, batch: int, frames: int, encoder_hidden_states):
+        """Once per video, before the denoising loop: every reader block projects its ReferenceNet bank to K/V and
+        evaluates its (query-independent) attn2 constant, so that the per-step forward — typically replayed from a CUDA
+        graph — contains none of this step-invariant work."""
+        from .blocks import BasicTransformerBlock
+        ehs = encoder_hidden_states.to(torch.float16).contiguous()
+        ctx = RunCtx(batch, frames, None, ehs, ehs_key=None)
+        for m in self.modules():
+            if isinstance(m, BasicTransformerBlock):
+                m.prepare(ctx)
+
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, pose_cond_fea=None,
                 attention_mask=None, down_block_additional_residuals=None, mid_block_additional_residual=None,
                 return_dict: bool = True):

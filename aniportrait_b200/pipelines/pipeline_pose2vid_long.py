@@ -55,6 +55,8 @@ class Pose2VideoPipeline:
                                                       do_normalize=True)
         self.timings = {}
         self.use_cuda_graph = True   # capture the per-window UNet step once, replay it every DDIM step
+        self._warmed = set()
+        self._side_stream = None
 
     # -------------------------------------------------------------------------------------------- plumbing
     def _nn_modules(self):
@@ -118,6 +120,17 @@ class Pose2VideoPipeline:
     def decode_latents(self, latents: torch.Tensor):
         """Reference-compatible: numpy fp32 on the host (reference :113-126)."""
         return self.decode_latents_device(latents).cpu().float().numpy()
+
+    def _pose_maps_to_tensor(self, pose_images, height, width, device):
+        """cond_image_processor.preprocess for the pose maps. uint8 HxWx3 arrays of the target size (what the scripts
+        pass, pose2vid.py:153-158) take a fast path: the bytes go to the GPU and the reference's `2*x - 1` (no /255, see
+        image_processor.py) is evaluated there in fp32 — identical values, 4x fewer bytes over PCIe, no host float pass."""
+        frames = list(pose_images)
+        if all(isinstance(p, np.ndarray) and p.dtype == np.uint8 and p.ndim == 3 and p.shape[:2] == (height, width)
+               for p in frames):
+            u8 = torch.from_numpy(np.ascontiguousarray(np.stack(frames, 0))).to(device, non_blocking=True)
+            return u8.permute(0, 3, 1, 2).to(torch.float32) * 2.0 - 1.0
+        return torch.cat([self.cond_image_processor.preprocess(p, height=height, width=width) for p in frames], dim=0)
 
     def _broadcast_banks(self, writer, device):
         """NCCL broadcast (rank 0 -> all) of the ReferenceNet banks: 16 tensors [dup, N, C] fp16, ~46 MB at 512x512."""
@@ -215,13 +228,19 @@ class Pose2VideoPipeline:
             ops.scatter_accumulate(pred, idx, acc)
 
         graphs = []
+        self.denoising_unet.prepare_reference(dup, len(my_windows[0]) if my_windows else context_frames, ehs)
         if self.use_cuda_graph and len(win_idx) > 0:
             t_dev.fill_(float(timesteps[0]))
-            side = torch.cuda.Stream(device=device)
+            side = self._side_stream if getattr(self, "_side_stream", None) is not None else torch.cuda.Stream(device=device)
+            self._side_stream = side
             side.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(side):
-                window_step(win_idx[0], win_pose[0])       # warm-up: one-time caches, kernel attributes, workspaces
-                acc.zero_()
+            warm_key = (L, h, w, dup, tuple(len(wd) for wd in my_windows))
+            if warm_key not in self._warmed:
+                with torch.cuda.stream(side):
+                    # first use of these shapes: one eager pass sets kernel attributes / workspaces / weight packing
+                    window_step(win_idx[0], win_pose[0])
+                    acc.zero_()
+                self._warmed.add(warm_key)
             torch.cuda.current_stream(device).wait_stream(side)
             pool = None
             for idx, pose_fea in zip(win_idx, win_pose):
@@ -313,8 +332,7 @@ class Pose2VideoPipeline:
         latents = self.prepare_latents(num_images_per_prompt, self.denoising_unet.in_channels, width, height,
                                        video_length, embed_dtype, device, generator, latents)
         ref_image_tensor = self.ref_image_processor.preprocess(ref_image, height=height, width=width)
-        pose_list = [self.cond_image_processor.preprocess(p, height=height, width=width) for p in pose_images]
-        pose_cond = torch.cat(pose_list, dim=0)                                               # [L, 3, H, W] (host)
+        pose_cond = self._pose_maps_to_tensor(pose_images, height, width, device)            # [L, 3, H, W]
         video = self.run_device(clip_pixels, ref_image_tensor, pose_cond, latents, num_inference_steps,
                                 guidance_scale, context_schedule, context_frames, context_stride, context_overlap,
                                 callback, callback_steps, clip_image_embeds, dist_mode)
