@@ -51,6 +51,7 @@ struct GemmParams {
   // TMA epilogue (per-warp 32-row x 32-column boxes staged in 64B-swizzled shared memory)
   int tma_epi;             // 1: outputs leave through TMA stores, the residual arrives through TMA loads
   int sub_w, sub_h, sub_n; // conv modes: geometry of a warp's 32-row sub-box
+  int debug;               // AP_GEMM_DEBUG: 1 = skip TMA loads (MMA pace), 2 = skip MMAs (TMA pace); results are garbage
 };
 
 template <int BN, int CG = 1>
@@ -145,11 +146,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane
+    // issues; tap / channel-block indices advance incrementally instead of by per-k-block integer division)
+    {
       int stage = 0;
       uint32_t phase = 0;
-      const int kb_per_tap = p.kb_src1 + p.kb_src2;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
         const int n_tile = tile % p.num_n_tiles;
@@ -162,34 +163,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           y0 = (rem / p.tiles_x) * p.bh;
           x0 = (rem % p.tiles_x) * p.bw;
         }
+        int within = 0, kx = 0, ky = 0;   // channel block inside the tap; tap = (ky, kx)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          // CG == 2: only the leader arms its barrier, with the bytes of BOTH CTAs (their TMA loads signal it)
-          if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
-          void* a_dst = smem_a + stage * Cfg::A_BYTES;
-          void* b_dst = smem_b + stage * Cfg::B_BYTES;
-          const int tap = kb / kb_per_tap;
-          const int within = kb % kb_per_tap;
-          const bool second = within >= p.kb_src1;
-          const CUtensorMap* am = second ? &tmA2 : &tmA1;
-          const int c0 = (second ? within - p.kb_src1 : within) * Cfg::BK;
-          if (p.a_mode == A_GEMM) {
-            if (CG == 2) tma_load_2d_2sm(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
-            else tma_load_2d(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
-          } else if (p.a_mode == A_CONV_S1) {
-            const int ky = tap / 3, kx = tap % 3;
-            if (CG == 2) tma_load_4d_2sm(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
-            else tma_load_4d(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
-          } else {
-            // input pixel = 2*o + k - 1  ->  k=0: (o-1, phase 1), k=1: (o, phase 0), k=2: (o, phase 1)
-            const int ky = tap / 3, kx = tap % 3;
-            const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
-            const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
-            if (CG == 2) tma_load_5d_2sm(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
-            else tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
+          if (elect_one()) {
+            if (p.debug == 1) {   // timing experiment: no loads at all, the MMA consumes stale shared memory
+              if (CG == 1 || cta_rank == 0) mbar_arrive(&full_bar[stage]);
+            } else {
+            // CG == 2: only the leader arms its barrier, with the bytes of BOTH CTAs (their TMA loads signal it)
+            if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
+            void* a_dst = smem_a + stage * Cfg::A_BYTES;
+            void* b_dst = smem_b + stage * Cfg::B_BYTES;
+            const bool second = within >= p.kb_src1;
+            const CUtensorMap* am = second ? &tmA2 : &tmA1;
+            const int c0 = (second ? within - p.kb_src1 : within) * Cfg::BK;
+            if (p.a_mode == A_GEMM) {
+              if (CG == 2) tma_load_2d_2sm(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
+              else tma_load_2d(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
+            } else if (p.a_mode == A_CONV_S1) {
+              if (CG == 2) tma_load_4d_2sm(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
+              else tma_load_4d(am, &full_bar[stage], a_dst, c0, x0 + kx - 1, y0 + ky - 1, n0);
+            } else {
+              // input pixel = 2*o + k - 1  ->  k=0: (o-1, phase 1), k=1: (o, phase 0), k=2: (o, phase 1)
+              const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
+              const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
+              if (CG == 2) tma_load_5d_2sm(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
+              else tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
+            }
+            if (CG == 2)
+              tma_load_2d_2sm(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN + (int)cta_rank * (BN / 2));
+            else
+              tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
+            }
           }
-          if (CG == 2) tma_load_2d_2sm(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN + (int)cta_rank * (BN / 2));
-          else tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
+          __syncwarp();
+          if (++within == p.kb_src1 + p.kb_src2) {
+            within = 0;
+            if (++kx == 3) { kx = 0; ++ky; }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -215,6 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           const uint64_t da = umma_desc_k_sw128(a_base + stage * Cfg::A_BYTES);
           const uint64_t db = umma_desc_k_sw128(b_base + stage * Cfg::B_BYTES);
           if (elect_one()) {
+            if (p.debug != 2)
 #pragma unroll
             for (int k = 0; k < Cfg::BK / 16; ++k) {
               // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in the (>>4) start-address field
@@ -749,6 +761,7 @@ extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2
   p.out = (__half*)out;
   p.ldo = (int)ldo;
   p.n_valid = n_valid > 0 ? n_valid : Cout;
+  p.debug = getenv("AP_GEMM_DEBUG") ? atoi(getenv("AP_GEMM_DEBUG")) : 0;
 
   auto make_act_map = [&](CUtensorMap* tm, const void* base, int C) -> int {
     if (stride == 1) {
