@@ -37,6 +37,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -1351,6 +1359,301 @@ static int launch_attention4(const CUtensorMap* maps, const AttnParams& p, cudaS
   return AP_OK;
 }
 
+
+// ============================================================================================================
+// v5: ONE 128-query tile per CTA, TWO CTAs per SM. S is double-buffered in TMEM (Q.K^T of key tile j+1 is issued before
+// the softmax of tile j finishes, so the softmax warps are decoupled from the softmax -> P.V -> Q.K^T chain that costs
+// v3 ~900 idle cycles per tile), P goes back into its own S buffer (tcgen05.st) and P.V reads it from TMEM (TS form).
+// Key tiles of 96 keep the allocation at 256 TMEM columns (S0 [0,96), S1 [96,192), O [192,256)) and ~90 KB of shared
+// memory, so two CTAs (2 x 4 softmax warps = two per SM sub-partition) co-reside and hide each other's latencies.
+// Only for DPAD = 64 (d <= 64: the 64x64-resolution layers, 88 % of the attention FLOPs).
+// ============================================================================================================
+struct Attn5Cfg {
+  static constexpr int DPAD = 64, BN = 96;
+  static constexpr int Q_BYTES = 128 * 128;            // 128 rows x 64 fp16
+  static constexpr int K_BYTES = BN * 128;
+  static constexpr int KV_STAGE = 2 * K_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * KV_STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_S0 = 0, TMEM_S1 = 96, TMEM_O = 192, TMEM_COLS = 256;
+  static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs must fit one SM");
+};
+
+__global__ void __launch_bounds__(192, 2)
+attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
+                  const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
+  using Cfg = Attn5Cfg;
+  constexpr int ST = Cfg::STAGES, BN = Cfg::BN, DPAD = Cfg::DPAD;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_kv = smem_q + Cfg::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ST * Cfg::KV_STAGE);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;            // [ST]
+  uint64_t* v_full = k_full + ST;         // [ST]
+  uint64_t* kv_empty = v_full + ST;       // [ST]
+  uint64_t* s_full = kv_empty + ST;       // [2] per S buffer
+  uint64_t* p_full = s_full + 2;          // [2] per S buffer
+  uint64_t* pv_done = p_full + 2;         // every P.V (rescale path only)
+  uint64_t* o_done = pv_done + 1;         // last P.V of a unit
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 4);
+    }
+    mbar_init(pv_done, 1);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int own_tiles = (p.tokens + BN - 1) / BN;
+  const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
+  const int units_per_frame = p.heads * p.m_tiles;
+
+  auto decode = [&](int unit, int& frame, int& head, int& m_tile, int& T) {
+    const int fk = unit / units_per_frame;
+    const int rem = unit % units_per_frame;
+    frame = (fk + p.first_bank_frame) % p.n_frames;
+    head = rem / p.m_tiles;
+    m_tile = rem % p.m_tiles;
+    const bool has_bank = p.bank_tokens > 0 && frame >= p.first_bank_frame;
+    T = own_tiles + (has_bank ? bank_tiles : 0);
+  };
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------------------- TMA producer
+    uint32_t g = 0, uc = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+      int frame, head, m_tile, T;
+      decode(unit, frame, head, m_tile, T);
+      mbar_wait(q_empty, (uc & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+        tma_load_2d(&tmQ, q_full, smem_q, head * DPAD, frame * p.tokens + m_tile * 128);
+      }
+      __syncwarp();
+      const int bank_idx = (frame - p.first_bank_frame) / p.frames_per_bank;
+      for (int j = 0; j < T; ++j, ++g) {
+        const int stage = g % ST;
+        mbar_wait(&kv_empty[stage], ((g / ST) & 1) ^ 1);
+        if (elect_one()) {
+          const bool own = j < own_tiles;
+          const CUtensorMap* mk = own ? &tmK : &tmBK;
+          const CUtensorMap* mv = own ? &tmV : &tmBV;
+          const int row = own ? frame * p.tokens + j * BN : bank_idx * p.bank_tokens + (j - own_tiles) * BN;
+          uint8_t* kd = smem_kv + stage * Cfg::KV_STAGE;
+          mbar_arrive_expect_tx(&k_full[stage], Cfg::K_BYTES);
+          tma_load_2d(mk, &k_full[stage], kd, head * DPAD, row);
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::K_BYTES);
+          tma_load_2d(mv, &v_full[stage], kd + Cfg::K_BYTES, head * DPAD, row);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------------------- MMA issuer (warp-uniform, elected lane)
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);
+    const uint32_t qa = smem_u32(smem_q);
+    uint32_t g = 0, uc = 0;
+    auto issue_qk = [&](uint32_t gi, bool last_of_unit) {
+      const int stage = gi % ST;
+      mbar_wait(&k_full[stage], (gi / ST) & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ((gi & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0);
+      const uint32_t ka = smem_u32(smem_kv + stage * Cfg::KV_STAGE);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DPAD / 16; ++kk)
+          umma_f16_ss(d_tmem, umma_desc_k_sw128(qa + kk * 32), umma_desc_k_sw128(ka + kk * 32), idesc_qk, kk != 0);
+        umma_commit(&s_full[gi & 1]);
+        if (last_of_unit) umma_commit(q_empty);
+      }
+      __syncwarp();
+    };
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+      int frame, head, m_tile, T;
+      decode(unit, frame, head, m_tile, T);
+      mbar_wait(q_full, uc & 1);
+      for (int j = 0; j < T; ++j, ++g) {
+        // S buffer (g+1)&1 last held P(g-1), consumed by P.V(g-1) which was issued earlier (tcgen05.mma runs in order)
+        if (j == 0) issue_qk(g, T == 1);
+        if (j + 1 < T) issue_qk(g + 1, j + 2 == T);
+        const int stage = g % ST;
+        mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+        mbar_wait(&v_full[stage], (g / ST) & 1);
+        tc_fence_after();
+        const uint32_t a_tmem = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0);   // P aliases its S buffer
+        const uint32_t va = smem_u32(smem_kv + stage * Cfg::KV_STAGE + Cfg::K_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk)
+            umma_f16_ts(tmem_base + Cfg::TMEM_O, a_tmem + kk * 8, umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128),
+                        idesc_pv, (j | kk) != 0);
+          umma_commit(&kv_empty[stage]);
+          umma_commit(pv_done);
+          if (j + 1 == T) umma_commit(o_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------------- softmax + epilogue
+    const int lane_group = warp & 3;
+    const int row = lane_group * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(lane_group * 32) << 16;
+    const uint32_t t_o = tmem_base + Cfg::TMEM_O + t_lane;
+    uint32_t g = 0, uc = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
+      int frame, head, m_tile, T;
+      decode(unit, frame, head, m_tile, T);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < T; ++j, ++g) {
+        const uint32_t t_s = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t sr[BN];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+        tmem_ld_wait();
+
+        const bool own = j < own_tiles;
+        const int jj = own ? j : j - own_tiles;
+        const int ntok = own ? p.tokens : p.bank_tokens;
+        const int valid = min(BN, ntok - jj * BN);
+        if (valid != BN) {
+#pragma unroll
+          for (int i = 0; i < BN; ++i)
+            if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
+        }
+        float mx8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+#pragma unroll
+        for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sr[i]));
+        float tmax = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                           fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        tmax *= p.scale_log2;
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_run = tmax;
+        } else if (tmax > m_run + kRescaleThreshold) {
+          alpha = fast_exp2(m_run - tmax);
+          m_run = tmax;
+          need = true;
+        }
+        const bool warp_need = __any_sync(0xffffffffu, need);
+        l_run *= alpha;
+        if (warp_need) {   // rare: O may only be touched once P.V of the previous key tile has completed
+          mbar_wait(pv_done, (g - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DPAD / 32; ++c) {
+            uint32_t orr[32];
+            tmem_ld_32x32b_x32(t_o + c * 32, orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + c * 32, orr);
+          }
+        }
+        uint32_t pk[BN / 2];
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < BN; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
+          ls[(i >> 1) & 3] += p0 + p1;
+          const __half2 h = __floats2half2_rn(p0, p1);
+          pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        // P (48 packed columns) -> TMEM over the first half of this S buffer
+        tmem_st_32x32b_x32(t_s, pk);
+        tmem_st_32x32b_x16(t_s + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+      }
+      // ------------------------------------------------------------------ epilogue
+      mbar_wait(o_done, uc & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const int q_idx = m_tile * 128 + row;
+      const bool row_ok = q_idx < p.tokens;
+      __half* dst = p.out + ((long long)frame * p.tokens + q_idx) * p.ldo + head * p.head_dim;
+#pragma unroll 1
+      for (int c = 0; c < DPAD / 32; ++c) {
+        if (c * 32 >= p.head_dim) break;
+        uint32_t orr[32];
+        tmem_ld_32x32b_x32(t_o + c * 32, orr);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c * 32 + q * 8 < p.head_dim) {
+              __half2 o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = __floats2half2_rn(__uint_as_float(orr[q * 8 + 2 * i]) * inv_l,
+                                         __uint_as_float(orr[q * 8 + 2 * i + 1]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = *reinterpret_cast<uint4*>(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+static int launch_attention5(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
+  using Cfg = Attn5Cfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(attention5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int max_ctas = 2 * num_sms();
+  const int grid = p.num_units < max_ctas ? p.num_units : max_ctas;
+  attention5_kernel<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
 template <int DPAD, int BN>
 static int launch_attention2(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = Attn2Cfg<DPAD, BN>;
@@ -1405,11 +1708,13 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
   // v4 (double-buffered S, 64-key tiles) measured slower than v3 (3.56 vs 2.67 ms on the 64x64 level: the per-tile fixed
   // costs double) and is kept selectable (AP_ATTENTION_V4=1) for further tuning only.
   static const bool force_v4 = (getenv("AP_ATTENTION_V4") != nullptr);
+  static const int v5_env = getenv("AP_ATTENTION_V5") ? atoi(getenv("AP_ATTENTION_V5")) : -1;
   const bool two_tiles = !force_v1 && dpad <= 128 && tokens > 128;
-  const bool use_v4 = two_tiles && force_v4;
-  const bool use_v3 = two_tiles && !force_v2 && !force_v4;
+  const bool use_v5 = (v5_env == 1) && !force_v1 && dpad == 64 && tokens > 128;
+  const bool use_v4 = two_tiles && force_v4 && !use_v5;
+  const bool use_v3 = two_tiles && !force_v2 && !force_v4 && !use_v5;
   const bool use_v2 = two_tiles && force_v2;
-  const int bn = use_v4 ? 64 : (use_v3 ? 128 : (use_v2 ? (dpad == 64 ? 128 : 64) : (dpad == 192 ? 64 : 128)));
+  const int bn = use_v5 ? 96 : use_v4 ? 64 : (use_v3 ? 128 : (use_v2 ? (dpad == 64 ? 128 : 64) : (dpad == 192 ? 64 : 128)));
 
   AttnParams p{};
   p.n_frames = n_frames;
@@ -1451,6 +1756,7 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
     maps[4] = maps[2];
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_v5) return launch_attention5(maps, p, st);
   if (use_v4) {
     static const int emu_env4 = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : -1;
     const int emu = emu_env4 >= 0 ? emu_env4 : 0;
