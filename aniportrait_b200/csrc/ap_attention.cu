@@ -1379,6 +1379,7 @@ struct Attn5Cfg {
   static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs must fit one SM");
 };
 
+template <int EMU_NUM, bool DENOM, bool PREFETCH>
 __global__ void __launch_bounds__(192, 2)
 attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
@@ -1527,19 +1528,28 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t t_lane = static_cast<uint32_t>(lane_group * 32) << 16;
     const uint32_t t_o = tmem_base + Cfg::TMEM_O + t_lane;
     uint32_t g = 0, uc = 0;
+    uint32_t sr[BN];
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
       int frame, head, m_tile, T;
       decode(unit, frame, head, m_tile, T);
       float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < T; ++j, ++g) {
-        const uint32_t t_s = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
+      if (PREFETCH) {   // S of the unit's first key tile; later tiles are fetched while the previous P store drains
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        uint32_t sr[BN];
+        const uint32_t t_s0 = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s0 + c * 32, sr + c * 32);
         tmem_ld_wait();
-
+      }
+      for (int j = 0; j < T; ++j, ++g) {
+        const uint32_t t_s = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
+        if (!PREFETCH) {
+          mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+          tmem_ld_wait();
+        }
         const bool own = j < own_tiles;
         const int jj = own ? j : j - own_tiles;
         const int ntok = own ? p.tokens : p.bank_tokens;
@@ -1567,7 +1577,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           need = true;
         }
         const bool warp_need = __any_sync(0xffffffffu, need);
-        l_run *= alpha;
+        if (!DENOM) l_run *= alpha;
         if (warp_need) {   // rare: O may only be touched once P.V of the previous key tile has completed
           mbar_wait(pv_done, (g - 1) & 1);
           tc_fence_after();
@@ -1585,24 +1595,42 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < BN; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
-          ls[(i >> 1) & 3] += p0 + p1;
+          const bool emu = (EMU_NUM > 0) && (((i >> 1) & 3) < EMU_NUM);
+          const float a0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run);
+          const float a1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run);
+          const float p0 = emu ? poly_exp2(a0) : fast_exp2(a0);
+          const float p1 = emu ? poly_exp2(a1) : fast_exp2(a1);
+          if (!DENOM) ls[(i >> 1) & 3] += p0 + p1;
           const __half2 h = __floats2half2_rn(p0, p1);
           pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        if (!DENOM) l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         // P (48 packed columns) -> TMEM over the first half of this S buffer
         tmem_st_32x32b_x32(t_s, pk);
         tmem_st_32x32b_x16(t_s + 32, pk + 32);
+        if (PREFETCH && j + 1 < T) {   // fetch S of the next key tile while the P store drains
+          const uint32_t gn = g + 1;
+          mbar_wait(&s_full[gn & 1], (gn >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t_sn = tmem_base + ((gn & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_sn + c * 32, sr + c * 32);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g & 1]);
+        if (PREFETCH && j + 1 < T) tmem_ld_wait();
       }
       // ------------------------------------------------------------------ epilogue
       mbar_wait(o_done, uc & 1);
       tc_fence_after();
+      if (DENOM) {   // V carries 1.0 in padded column head_dim: that accumulator column is sum_j P_ij
+        uint32_t lv[1];
+        tmem_ld_32x32b_x1(t_o + p.head_dim, lv);
+        tmem_ld_wait();
+        l_run = __uint_as_float(lv[0]);
+      }
       const float inv_l = 1.f / l_run;
       const int q_idx = m_tile * 128 + row;
       const bool row_ok = q_idx < p.tokens;
@@ -1640,16 +1668,18 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+template <int EMU_NUM, bool DENOM, bool PREFETCH>
 static int launch_attention5(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = Attn5Cfg;
   static bool attr_set = false;
+  auto kern = attention5_kernel<EMU_NUM, DENOM, PREFETCH>;
   if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(attention5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int max_ctas = 2 * num_sms();
   const int grid = p.num_units < max_ctas ? p.num_units : max_ctas;
-  attention5_kernel<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -1692,7 +1722,8 @@ using namespace ap;
 extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, long long ld_qkv, const void* bank_k,
                                 const void* bank_v, long long ld_bank, int bank_tokens, int n_banks, int n_frames,
                                 int tokens, int heads, int head_dim, int dpad, int first_bank_frame,
-                                int frames_per_bank, float scale, void* out, long long ldo, void* stream) {
+                                int frames_per_bank, float scale, void* out, long long ldo, int flags,
+                                void* stream) {
   AP_REQUIRE(q && k && v && out, "attention: null pointer");
   AP_REQUIRE(dpad == 64 || dpad == 128 || dpad == 192, "attention: dpad must be 64/128/192 (got %d)", dpad);
   AP_REQUIRE(head_dim % 8 == 0 && head_dim <= dpad, "attention: head_dim %d must be a multiple of 8 and <= dpad", head_dim);
@@ -1710,7 +1741,7 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
   static const bool force_v4 = (getenv("AP_ATTENTION_V4") != nullptr);
   static const int v5_env = getenv("AP_ATTENTION_V5") ? atoi(getenv("AP_ATTENTION_V5")) : -1;
   const bool two_tiles = !force_v1 && dpad <= 128 && tokens > 128;
-  const bool use_v5 = (v5_env == 1) && !force_v1 && dpad == 64 && tokens > 128;
+  const bool use_v5 = (v5_env != 0) && !force_v1 && !force_v2 && !force_v4 && dpad == 64 && tokens > 128;
   const bool use_v4 = two_tiles && force_v4 && !use_v5;
   const bool use_v3 = two_tiles && !force_v2 && !force_v4 && !use_v5;
   const bool use_v2 = two_tiles && force_v2;
@@ -1756,7 +1787,18 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
     maps[4] = maps[2];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_v5) return launch_attention5(maps, p, st);
+  if (use_v5) {
+    // A/B switches kept for profiling: AP_ATTENTION_EMU=1 evaluates 1/4 of the exponentials on the FMA pipe,
+    // AP_ATTENTION_PREFETCH=1 fetches S(j+1) under the P(j) store, AP_ATTENTION_NO_DENOM=1 ignores the V ones column
+    // (all three measured slower or equal on B200, see profiles/r01_ncu_full_top_kernels.md).
+    static const int emu5 = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : 0;
+    static const bool prefetch = getenv("AP_ATTENTION_PREFETCH") != nullptr;
+    static const bool no_denom = getenv("AP_ATTENTION_NO_DENOM") != nullptr;
+    const bool denom = (flags & AP_ATTN_DENOM_IN_V) != 0 && head_dim < dpad && !no_denom;
+    if (prefetch) return denom ? launch_attention5<0, true, true>(maps, p, st) : launch_attention5<0, false, true>(maps, p, st);
+    if (emu5 == 1) return denom ? launch_attention5<1, true, false>(maps, p, st) : launch_attention5<1, false, false>(maps, p, st);
+    return denom ? launch_attention5<0, true, false>(maps, p, st) : launch_attention5<0, false, false>(maps, p, st);
+  }
   if (use_v4) {
     static const int emu_env4 = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : -1;
     const int emu = emu_env4 >= 0 ? emu_env4 : 0;
