@@ -10,12 +10,14 @@ Same constructor and `__call__` signature and the same result object (`.videos`:
     CFG-duplicated batch every step, :531-536) — identical values, 25x less work;
   * ReferenceNet runs once; each reader block projects its bank to K/V once per video;
   * VAE decode is batched over frames (reference: one frame per call, :118-121).
-With torch.distributed initialised and `dist_mode` set, frame windows are sharded across ranks: rank 0 runs the
-ReferenceNet once and broadcasts the 16 banks over NCCL; "windows" mode additionally all-reduces the fp32 prediction
-accumulator once per step. There is no collective inside any kernel's critical path.
+  * all of the above is captured into CUDA graphs once per video geometry and replayed for every later video.
+With torch.distributed initialised, dist_mode="windows" shards the frame windows of one video across ranks: rank 0 runs
+the ReferenceNet once and broadcasts the 16 banks over NCCL, and the fp32 prediction accumulator is all-reduced once per
+step; dist_mode="clips" gives every rank its own clip with no data-path collective at all.
 """
 from __future__ import annotations
 
+import time
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Union
 
@@ -26,6 +28,19 @@ from .. import ops
 from ..models.mutual_self_attention import ReferenceAttentionControl
 from .sharding import plan_windows, windows_of_rank
 from .image_processor import VaeImageProcessor
+
+
+class _Session:
+    """Tensors one video's stages communicate through (inputs, latents, accumulator, banks' owners, pose features) and, for
+    static sessions, the CUDA graphs captured over them."""
+
+
+def _assign(dst, src):
+    """First pass: keep the tensor; later passes (incl. graph capture): write into the same storage."""
+    if dst is None:
+        return src.contiguous().clone()
+    dst.copy_(src)
+    return dst
 
 
 @dataclass
@@ -54,8 +69,10 @@ class Pose2VideoPipeline:
         self.cond_image_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor, do_convert_rgb=True,
                                                       do_normalize=True)
         self.timings = {}
-        self.use_cuda_graph = True   # capture the per-window UNet step once, replay it every DDIM step
-        self._warmed = set()
+        self.use_cuda_graph = True        # capture every stage of a video geometry once (a _Session), replay afterwards
+        self.capture_library_stage = True  # also capture CLIP + VAE-encode (falls back to eager if not capturable)
+        self.max_sessions = 2
+        self._sessions = {}
         self._side_stream = None
 
     # -------------------------------------------------------------------------------------------- plumbing
@@ -156,6 +173,134 @@ class Pose2VideoPipeline:
         a_p = float(sch.alphas_cumprod[prev]) if prev >= 0 else float(sch.final_alpha_cumprod)
         return a_t, a_p
 
+    # -------------------------------------------------------------------------------------------- per-video stages
+    # The work of one video is split into stages that only read / write the tensors of a _Session, so that each stage can
+    # either run eagerly or be captured once into a CUDA graph and replayed for every later video of the same geometry.
+    def _stage_embed(self, S):
+        """Library modules: CLIP image embedding -> encoder_hidden_states; reference image -> VAE latent (once per video)."""
+        if S.clip_is_embed:
+            emb = S.clip_in
+        else:
+            emb = self.image_encoder(S.clip_in).image_embeds
+        ehs = emb.unsqueeze(1)
+        if S.dup == 2:
+            ehs = torch.cat([torch.zeros_like(ehs), ehs], dim=0)
+        S.ehs = _assign(S.ehs, ehs.to(torch.float16))
+        S.ref_latents = _assign(S.ref_latents, self.vae.encode(S.ref_image).latent_dist.mean * 0.18215)
+
+    def _stage_reference_write(self, S):
+        """ReferenceNet write pass (once per video): every spatial block appends norm1(x) to its bank."""
+        self.reference_unet(S.ref_latents.repeat(S.dup, 1, 1, 1), torch.zeros((), device=S.lat.device),
+                            encoder_hidden_states=S.ehs, return_dict=False)
+
+    def _stage_reference_read(self, S):
+        """Banks -> reader blocks (+ their K/V projections and attn2 constants); pose maps -> PoseGuider once per window."""
+        S.reader.update(S.writer)
+        S.win_pose = []
+        for idx in S.win_idx_long:
+            fea = self.pose_guider.forward_nhwc(S.pose_cond.index_select(0, idx))
+            S.win_pose.append([f.to(torch.float16).contiguous() for f in fea])
+        self.denoising_unet.prepare_reference(S.dup, S.frames0, S.ehs)
+
+    def _window_step(self, S, k):
+        idx = S.win_idx[k]
+        x = ops.gather_window(S.lat, idx, S.dup, 64)
+        pred = self.denoising_unet.forward_nhwc(x, S.dup, idx.numel(), S.t_dev, S.ehs, S.win_pose[k])
+        ops.scatter_accumulate(pred, idx, S.acc)
+
+    def _reset_block_caches(self):
+        """Drop step-invariant tensors cached on the transformer blocks (bank K/V, attn2 constants) so that the next pass
+        recomputes them — required right before a graph capture, otherwise the work would be missing from the graph."""
+        from ..models.blocks import BasicTransformerBlock
+        for net in (self.reference_unet, self.denoising_unet, self.pose_guider):
+            for m in net.modules():
+                if isinstance(m, BasicTransformerBlock):
+                    m._bank_kv = None
+                    m._attn2_const = None
+
+    def _weights_fingerprint(self):
+        return hash(tuple((p.data_ptr(), p._version) for m in self._nn_modules() for p in m.parameters()))
+
+    def _new_session(self, clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, static):
+        device = self.device
+        S = _Session()
+        S.clip_is_embed, S.dup, S.static = clip_is_embed, dup, static
+        enc_dtype = self.image_encoder.dtype if isinstance(self.image_encoder, torch.nn.Module) else torch.float16
+
+        def own(t, dtype):   # static sessions own their input buffers (graphs read them on every replay)
+            t = t.to(device=device, dtype=dtype)
+            return t.clone() if static else t
+        S.clip_in = own(clip_in, torch.float16 if clip_is_embed else enc_dtype)
+        S.ref_image = own(ref_image_tensor, self.vae.dtype)
+        S.pose_cond = own(pose_cond, self.pose_guider.dtype)
+        S.lat = torch.empty(L, h, w, 4, dtype=torch.float16, device=device)
+        S.acc = torch.zeros(dup, L, h, w, 4, dtype=torch.float32, device=device)
+        S.t_dev = torch.zeros(1, dtype=torch.float32, device=device)
+        S.ehs = S.ref_latents = S.win_pose = None
+        S.win_idx = [torch.tensor(wd, dtype=torch.int32, device=device) for wd in my_windows]
+        S.win_idx_long = [i.long() for i in S.win_idx]
+        S.frames0 = len(my_windows[0]) if my_windows else 16
+        cfg = dup == 2
+        S.writer = ReferenceAttentionControl(self.reference_unet, do_classifier_free_guidance=cfg, mode="write",
+                                             batch_size=1, fusion_blocks="full")
+        S.reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=cfg, mode="read",
+                                             batch_size=1, fusion_blocks="full")
+        S.g_embed = S.g_reference = None
+        S.g_windows = []
+        S.n_embed = S.n_reference = 0
+        S.n_windows = []
+        return S
+
+    def _capture(self, fn, pool=None):
+        """Capture fn() on the side stream; returns (graph, number of this library's kernels recorded in it)."""
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.KERNEL_LAUNCHES
+        with torch.cuda.graph(g, pool=pool, stream=self._side_stream):
+            fn()
+        n = ops.KERNEL_LAUNCHES - n0
+        ops.KERNEL_LAUNCHES = n0     # recorded, not launched: replays are what count
+        return g, n
+
+    def _build_static_session(self, S, mark):
+        """First video of a geometry: one eager pass (lazy initialisation: cuDNN plans, kernel attributes, weight packing),
+        then every stage is captured. Later videos only copy their inputs into S and replay."""
+        device = self.device
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=device)
+        side = self._side_stream
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            self._stage_embed(S)
+            self._stage_reference_write(S)
+            self._stage_reference_read(S)
+            if S.win_idx:
+                self._window_step(S, 0)
+            S.acc.zero_()
+            S.reader.clear()
+            S.writer.clear()
+        torch.cuda.current_stream(device).wait_stream(side)
+        mark("warm_pass_ms")
+        self._reset_block_caches()
+        if self.capture_library_stage:
+            try:
+                S.g_embed, S.n_embed = self._capture(lambda: self._stage_embed(S))
+            except Exception as e:   # a library module that cannot be captured: keep that stage eager
+                import warnings
+                warnings.warn(f"CLIP / VAE-encode stage not graph-capturable ({type(e).__name__}: {e}); running it eagerly")
+                S.g_embed = None
+                torch.cuda.synchronize(device)
+
+        def reference():
+            self._stage_reference_write(S)
+            self._stage_reference_read(S)
+        S.g_reference, S.n_reference = self._capture(reference)
+        pool = S.g_reference.pool()
+        for k in range(len(S.win_idx)):
+            g, n = self._capture(lambda k=k: self._window_step(S, k), pool=pool)
+            S.g_windows.append(g)
+            S.n_windows.append(n)
+        mark("graph_capture_ms")
+
     # -------------------------------------------------------------------------------------------- device core
     @torch.no_grad()
     def run_device(self, clip_pixels, ref_image_tensor, pose_cond, latents, num_inference_steps, guidance_scale,
@@ -164,10 +309,24 @@ class Pose2VideoPipeline:
         """The hot path on device-resident inputs.
         clip_pixels [1,3,224,224] (or clip_image_embeds [1,768]); ref_image_tensor [1,3,H,W] in [-1,1];
         pose_cond [L,3,H,W] (pose maps as the reference's cond_image_processor emits them); latents [1,4,L,h,w].
-        Returns the decoded video on the device, fp16 [1,3,L,H,W] in [0,1] (None if decode=False)."""
+        Returns the decoded video on the device, fp16 [1,3,L,H,W] in [0,1] (None if decode=False).
+
+        Single GPU and dist_mode="clips": all stages of a video geometry are captured into CUDA graphs once (a cached
+        _Session) and replayed for every later video. dist_mode="windows" runs eagerly (NCCL bank broadcast + per-step
+        all-reduce between the stages); its per-window UNet call is GPU-bound even when launched from Python."""
         device = self.device
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
+        detail = {} if getattr(self, "profile_phases", False) else None
+        t_mark = [time.perf_counter()]
+
+        def mark(name):   # dev aid: synchronising wall-clock split of the per-video phase (off by default)
+            if detail is not None:
+                torch.cuda.synchronize(device)
+                now = time.perf_counter()
+                detail[name] = detail.get(name, 0.0) + (now - t_mark[0]) * 1e3
+                t_mark[0] = now
+        self.phase_detail = detail
         cfg = guidance_scale > 1.0
         dup = 2 if cfg else 1
         self.scheduler.set_timesteps(num_inference_steps, device=device)
@@ -175,91 +334,68 @@ class Pose2VideoPipeline:
         rank, world = 0, 1
         if dist_mode is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-
-        # CLIP image embedding (once per video; library module) --------------------------------------------
-        if clip_image_embeds is None:
-            clip_image_embeds = self.image_encoder(clip_pixels.to(device, dtype=self.image_encoder.dtype)).image_embeds
-        ehs = clip_image_embeds.to(device).unsqueeze(1)
-        if cfg:
-            ehs = torch.cat([torch.zeros_like(ehs), ehs], dim=0)
-        ehs = ehs.to(torch.float16).contiguous()
-
-        writer = ReferenceAttentionControl(self.reference_unet, do_classifier_free_guidance=cfg, mode="write",
-                                           batch_size=1, fusion_blocks="full")
-        reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=cfg, mode="read",
-                                           batch_size=1, fusion_blocks="full")
         if latents.shape[0] != 1:
             raise NotImplementedError("one video per call (the reference fixes batch_size = 1)")
         L, h, w = latents.shape[2], latents.shape[3], latents.shape[4]
-        lat = latents[0].permute(1, 2, 3, 0).to(torch.float16).contiguous()            # [L, h, w, 4]
-
-        # reference image -> VAE latent (once) -> ReferenceNet write pass (once) -------------------------
-        if world == 1 or rank == 0:
-            ref_image_latents = self.vae.encode(ref_image_tensor.to(dtype=self.vae.dtype, device=device)) \
-                .latent_dist.mean * 0.18215
-            self.reference_unet(ref_image_latents.repeat(dup, 1, 1, 1), torch.zeros((), device=device),
-                                encoder_hidden_states=ehs, return_dict=False)
-        if world > 1:
-            self._broadcast_banks(writer, device)
-        reader.update(writer)
-
-        # pose maps -> PoseGuider, once per window ------------------------------------------------------------
-        pose_cond = pose_cond.to(device=device, dtype=self.pose_guider.dtype)
         windows, inv_count = plan_windows(L, num_inference_steps, context_schedule, context_frames, context_stride,
                                           context_overlap)
         shard = world > 1 and dist_mode == "windows"
         my_windows = windows_of_rank(windows, rank, world, shard)
-        win_idx = [torch.tensor(wd, dtype=torch.int32, device=device) for wd in my_windows]
-        win_pose = []
-        for wd in my_windows:
-            fea = self.pose_guider.forward_nhwc(pose_cond[wd])
-            win_pose.append([f.to(torch.float16).contiguous() for f in fea])
         inv_count = inv_count.to(device=device, dtype=torch.float32)
-        acc = torch.zeros(dup, L, h, w, 4, dtype=torch.float32, device=device)
+        clip_is_embed = clip_image_embeds is not None
+        clip_in = clip_image_embeds if clip_is_embed else clip_pixels
+        static = bool(self.use_cuda_graph) and not shard
+
+        if static:
+            key = (L, h, w, dup, tuple(tuple(wd) for wd in my_windows), clip_is_embed, tuple(clip_in.shape),
+                   tuple(ref_image_tensor.shape), tuple(pose_cond.shape), self._weights_fingerprint())
+            S = self._sessions.get(key)
+            if S is None:
+                while len(self._sessions) >= self.max_sessions:     # each session pins ~10 GB of activations
+                    self._sessions.pop(next(iter(self._sessions)))
+                S = self._new_session(clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, True)
+                S.lat.copy_(latents[0].permute(1, 2, 3, 0))
+                self._build_static_session(S, mark)
+                self._sessions[key] = S
+            else:
+                S.clip_in.copy_(clip_in)
+                S.ref_image.copy_(ref_image_tensor)
+                S.pose_cond.copy_(pose_cond)
+                S.lat.copy_(latents[0].permute(1, 2, 3, 0))
+                S.acc.zero_()
+            if S.g_embed is not None:
+                S.g_embed.replay()
+                ops._count(S.n_embed)
+            else:
+                self._stage_embed(S)
+            S.g_reference.replay()
+            ops._count(S.n_reference)
+            mark("prologue_replay_ms")
+        else:
+            S = self._new_session(clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, False)
+            S.lat.copy_(latents[0].permute(1, 2, 3, 0))
+            self._stage_embed(S)
+            mark("embed_ms")
+            if world == 1 or rank == 0 or not shard:
+                self._stage_reference_write(S)
+            if shard:
+                self._broadcast_banks(S.writer, device)
+            self._stage_reference_read(S)
+            mark("reference_ms")
+        lat, acc = S.lat, S.acc
 
         # denoising loop -----------------------------------------------------------------------------------------
-        # Shapes are static, so the per-window work (gather -> ~800 kernel launches of the UNet -> scatter-accumulate)
-        # is captured once in a CUDA graph per window and replayed every step; only the timestep buffer changes.
-        t_dev = torch.zeros(1, dtype=torch.float32, device=device)
-
-        def window_step(idx, pose_fea):
-            x = ops.gather_window(lat, idx, dup, 64)
-            pred = self.denoising_unet.forward_nhwc(x, dup, idx.numel(), t_dev, ehs, pose_fea)
-            ops.scatter_accumulate(pred, idx, acc)
-
-        graphs = []
-        self.denoising_unet.prepare_reference(dup, len(my_windows[0]) if my_windows else context_frames, ehs)
-        if self.use_cuda_graph and len(win_idx) > 0:
-            t_dev.fill_(float(timesteps[0]))
-            side = self._side_stream if getattr(self, "_side_stream", None) is not None else torch.cuda.Stream(device=device)
-            self._side_stream = side
-            side.wait_stream(torch.cuda.current_stream(device))
-            warm_key = (L, h, w, dup, tuple(len(wd) for wd in my_windows))
-            if warm_key not in self._warmed:
-                with torch.cuda.stream(side):
-                    # first use of these shapes: one eager pass sets kernel attributes / workspaces / weight packing
-                    window_step(win_idx[0], win_pose[0])
-                    acc.zero_()
-                self._warmed.add(warm_key)
-            torch.cuda.current_stream(device).wait_stream(side)
-            pool = None
-            for idx, pose_fea in zip(win_idx, win_pose):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=side):
-                    window_step(idx, pose_fea)
-                pool = g.pool()
-                graphs.append(g)
-            acc.zero_()
         ev[1].record()
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
-                t_dev.fill_(float(t))
-                if graphs:
-                    for g in graphs:
+                S.t_dev.fill_(float(t))
+                if static:
+                    for g, n in zip(S.g_windows, S.n_windows):
                         g.replay()
+                        ops._count(n)
                 else:
-                    for idx, pose_fea in zip(win_idx, win_pose):
-                        window_step(idx, pose_fea)
+                    for k in range(len(S.win_idx)):
+                        self._window_step(S, k)
                 if shard:
                     torch.distributed.all_reduce(acc)
                 a_t, a_p = self._alpha_pair(t)
@@ -268,11 +404,14 @@ class Pose2VideoPipeline:
                 if callback is not None and i % callback_steps == 0:
                     callback(i, t, lat.permute(3, 0, 1, 2).unsqueeze(0))
         ev[2].record()
-        reader.clear()
-        writer.clear()
+        if not static:
+            S.reader.clear()
+            S.writer.clear()
 
         # decode ---------------------------------------------------------------------------------------------
         latents_out = lat.permute(3, 0, 1, 2).unsqueeze(0)                                # [1, 4, L, h, w]
+        if static:
+            latents_out = latents_out.clone()     # S.lat is overwritten by the next video
         self.last_latents = latents_out
         video = None
         if decode:
@@ -289,6 +428,10 @@ class Pose2VideoPipeline:
         self._events = ev
         self._meta = dict(windows=len(windows), steps=len(timesteps))
         return video
+
+    def clear_graph_cache(self):
+        """Drop every cached session (static buffers + CUDA graphs)."""
+        self._sessions.clear()
 
     def collect_timings(self):
         """Call after a synchronize: per-phase device times of the last run_device()."""
@@ -313,8 +456,9 @@ class Pose2VideoPipeline:
              None       every rank computes the whole video redundantly (reference behaviour)
              "windows"  the windows of ONE long video are sharded over ranks; fp32 prediction accumulator all-reduced
                         (NCCL) once per step; every rank ends with the full latents and video
-             "clips"    every rank denoises its OWN clip (its own pose_images / latents) of the same reference portrait
-           In both distributed modes rank 0 alone runs the ReferenceNet and broadcasts the 16 banks (NCCL)."""
+             "clips"    every rank denoises its OWN clip (its own pose_images / latents); fully independent ranks (the
+                        1 ms ReferenceNet pass is recomputed per rank rather than broadcast), no collective
+           In "windows" mode rank 0 alone runs the ReferenceNet and broadcasts the 16 banks (NCCL)."""
         if eta != 0.0:
             raise NotImplementedError("eta > 0 is unused by AniPortrait")
         if context_batch_size != 1:
