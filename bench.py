@@ -201,7 +201,7 @@ def kernel_rooflines(device, peaks):
     out = torch.empty(32, 64, 64, 320, device=device, dtype=torch.float16)
     ms = time_it(lambda: ops.conv3x3(x, wt, 320, bias=b, out=out))
     fl = 2.0 * 32 * 64 * 64 * 320 * 9 * 320
-    res["conv3x3"] = dict(kernel="gemm_kernel<160,LINEAR> (implicit-GEMM conv3x3 320->320 @64x64x32f)", ms=ms,
+    res["conv3x3"] = dict(kernel="gemm_kernel<BN=160,LINEAR,cta_group::2> (implicit-GEMM conv3x3 320->320 @64x64x32f)", ms=ms,
                           tflops=fl / ms / 1e9)
     # (2) fused reference attention, 64x64 level: 32 frames (16 uncond: N keys, 16 cond: 2N keys), 8 heads, d=40
     n, heads, d, dpad, fr = 4096, 8, 40, 64, 32
@@ -215,7 +215,7 @@ def kernel_rooflines(device, peaks):
                                        bank_k=bank[:, :hp], bank_v=bank[:, hp:], bank_tokens=n, n_banks=1,
                                        first_bank_frame=16, frames_per_bank=16, out=o, denom_in_v=True), iters=5)
     fl = 4.0 * n * d * heads * (16 * 2 * n + 16 * n)
-    res["ref_attention"] = dict(kernel="attention_kernel<64,128> (ref-attn 64x64 level, d=40, 16 cond + 16 uncond frames)",
+    res["ref_attention"] = dict(kernel="attention5_kernel (ref-attn 64x64 level, d=40 padded to 64, 16 cond + 16 uncond frames)",
                                 ms=ms, tflops=fl / ms / 1e9)
     # (3) one full UNet3D call is timed by the caller (aggregate)
     for v in res.values():
@@ -265,6 +265,9 @@ def run_product(args):
     def e2e_step():
         return pipe(ref_image, poses, ref_pose, W, H, L, DDIM_STEPS, GUIDANCE, generator=gen, dist_mode=dist_mode)
 
+    # dominant kernels timed alone (own launches, CUDA events on the launch stream) before the long run heats the part:
+    # the burst peak is their denominator; the whole-UNet-call figure below uses the sustained peak
+    roofs = kernel_rooflines(device, peaks) if rank == 0 else None
     for _ in range(args.warmup):
         device_step()
     barrier()
@@ -302,7 +305,6 @@ def run_product(args):
         e2e_value = world * L / (e2e_ms / 1e3)
         h2d = int(len(poses) * H * W * 3 + 3 * 224 * 224 * 4 + 3 * H * W * 4 + 4 * L * (H // 8) * (W // 8) * 2)
         d2h = int(3 * L * H * W * 2)
-        roofs = kernel_rooflines(device, peaks)
         unet_ms = phases["denoise_ms"] / DDIM_STEPS
         unet_tflops = FLOP_UNET_CALL / unet_ms / 1e9
         line = {
@@ -313,7 +315,7 @@ def run_product(args):
                                    "(BASELINE.json configs[1]); one 16-frame clip per GPU",
                        "weights": "random-init, real architecture sizes (UNet3D 1.31B params, sd-vae-ft-mse, CLIP ViT-L/14)",
                        "l2": "inputs larger than L2: 2.6 GB of weights + ~9 GB of activations stream per UNet call",
-                       "parallelism": f"dp{world} (frame-window shards; ReferenceNet banks broadcast once over NCCL)"
+                       "parallelism": f"dp{world} (one independent 16-frame clip per rank, no data-path collective)"
                        if world > 1 else "single GPU"},
             "e2e": {"value": round(e2e_value, 4), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3)},
