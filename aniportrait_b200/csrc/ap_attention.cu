@@ -1789,12 +1789,13 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
   cudaStream_t st = (cudaStream_t)stream;
   if (use_v5) {
     // A/B switches kept for profiling: AP_ATTENTION_EMU=1 evaluates 1/4 of the exponentials on the FMA pipe,
-    // AP_ATTENTION_PREFETCH=1 fetches S(j+1) under the P(j) store, AP_ATTENTION_NO_DENOM=1 ignores the V ones column
-    // (all three measured slower or equal on B200, see profiles/r01_ncu_full_top_kernels.md).
+    // AP_ATTENTION_PREFETCH=1 fetches S(j+1) under the P(j) store, AP_ATTENTION_DENOM=1 honours AP_ATTN_DENOM_IN_V
+    // (all three measured slower on B200 - 2.47 / 2.46 / 2.42 ms against 2.25 ms at the 64x64 level - see
+    // profiles/r01_ncu_full_top_kernels.md; the default therefore sums the probabilities on the CUDA cores).
     static const int emu5 = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : 0;
     static const bool prefetch = getenv("AP_ATTENTION_PREFETCH") != nullptr;
-    static const bool no_denom = getenv("AP_ATTENTION_NO_DENOM") != nullptr;
-    const bool denom = (flags & AP_ATTN_DENOM_IN_V) != 0 && head_dim < dpad && !no_denom;
+    static const bool use_denom = getenv("AP_ATTENTION_DENOM") != nullptr;
+    const bool denom = (flags & AP_ATTN_DENOM_IN_V) != 0 && head_dim < dpad && use_denom;
     if (prefetch) return denom ? launch_attention5<0, true, true>(maps, p, st) : launch_attention5<0, false, true>(maps, p, st);
     if (emu5 == 1) return denom ? launch_attention5<1, true, false>(maps, p, st) : launch_attention5<1, false, false>(maps, p, st);
     return denom ? launch_attention5<0, true, false>(maps, p, st) : launch_attention5<0, false, false>(maps, p, st);

@@ -197,10 +197,6 @@ class BasicTransformerBlock(nn.Module):
                      wo=f16(self.attn1.to_out[0].weight), bo=f32(self.attn1.to_out[0].bias),
                      g1=f32(self.norm1.weight), b1=f32(self.norm1.bias), g3=f32(self.norm3.weight),
                      b3=f32(self.norm3.bias))
-            # V's first padded column is set to 1 through the projection bias (to_q/k/v have none of their own), so the
-            # P.V accumulator carries the softmax denominator and the kernel skips the row sums
-            d["bqkv"] = ops.ones_column_bias(self.heads, self.dim_head, dpad, 3, 2, wq.device)
-            d["bkv"] = ops.ones_column_bias(self.heads, self.dim_head, dpad, 2, 1, wq.device)
             if self.attn2 is not None:
                 d.update(wv2=f16(self.attn2.to_v.weight), wo2=f16(self.attn2.to_out[0].weight),
                          bo2=f32(self.attn2.to_out[0].bias))
@@ -231,7 +227,7 @@ class BasicTransformerBlock(nn.Module):
         key = (bank.data_ptr(), bank._version, id(pk))
         if self._bank_kv is None or self._bank_kv[0] != key:
             nb = bank.shape[0]
-            kv = ops.gemm(bank.reshape(nb * bank.shape[1], bank.shape[2]).contiguous(), pk["wkv"], bias=pk["bkv"])
+            kv = ops.gemm(bank.reshape(nb * bank.shape[1], bank.shape[2]).contiguous(), pk["wkv"])
             self._bank_kv = (key, kv, nb)
         return self._bank_kv[1], self._bank_kv[2]
 
@@ -250,7 +246,7 @@ class BasicTransformerBlock(nn.Module):
         n1 = ops.layer_norm(t0, pk["g1"], pk["b1"])
         if self._ref_mode == "write":
             self.bank.append(n1.view(n_frames, tokens, self.dim).clone())
-        qkv = ops.gemm(n1, pk["wqkv"], bias=pk["bqkv"])
+        qkv = ops.gemm(n1, pk["wqkv"])
         q, k, v = qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:]
         kw = {}
         if self._ref_mode == "read" and len(self.bank) > 0:
@@ -270,7 +266,7 @@ class BasicTransformerBlock(nn.Module):
             else:
                 kw = dict(bank_k=kv[:, :hp], bank_v=kv[:, hp:], bank_tokens=bank_tokens, n_banks=nb,
                           first_bank_frame=0, frames_per_bank=ctx.F)
-        a = ops.attention(q, k, v, n_frames, tokens, heads, d, dpad, denom_in_v=pk["bqkv"] is not None, **kw)
+        a = ops.attention(q, k, v, n_frames, tokens, heads, d, dpad, **kw)
         bias, grouped = self._attn_out_bias(pk, ctx)
         t1 = ops.gemm(a, pk["wo"], bias=bias, residual=t0, bias_group_rows=(ctx.F * tokens if grouped else 0))
         n3 = ops.layer_norm(t1, pk["g3"], pk["b3"])

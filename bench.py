@@ -208,12 +208,10 @@ def kernel_rooflines(device, peaks):
     hp = heads * dpad
     qkv = torch.randn(fr * n, 3 * hp, device=device, dtype=torch.float16)
     bank = torch.randn(n, 2 * hp, device=device, dtype=torch.float16)
-    qkv.view(fr * n, 3, heads, dpad)[:, 2, :, d] = 1.0   # the model's layout: V carries the denominator column
-    bank.view(n, 2, heads, dpad)[:, 1, :, d] = 1.0
     o = torch.empty(fr * n, heads * d, device=device, dtype=torch.float16)
     ms = time_it(lambda: ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], fr, n, heads, d, dpad,
                                        bank_k=bank[:, :hp], bank_v=bank[:, hp:], bank_tokens=n, n_banks=1,
-                                       first_bank_frame=16, frames_per_bank=16, out=o, denom_in_v=True), iters=5)
+                                       first_bank_frame=16, frames_per_bank=16, out=o), iters=5)
     fl = 4.0 * n * d * heads * (16 * 2 * n + 16 * n)
     res["ref_attention"] = dict(kernel="attention5_kernel (ref-attn 64x64 level, d=40 padded to 64, 16 cond + 16 uncond frames)",
                                 ms=ms, tflops=fl / ms / 1e9)

@@ -19,8 +19,6 @@ n, heads, d, dpad, fr = 4096, 8, 40, 64, 32
 hp = heads * dpad
 qkv = torch.randn(fr * n, 3 * hp, device=dev, dtype=torch.float16)
 bank = torch.randn(n, 2 * hp, device=dev, dtype=torch.float16)
-qkv.view(fr * n, 3, heads, dpad)[:, 2, :, d] = 1.0
-bank.view(n, 2, heads, dpad)[:, 1, :, d] = 1.0
 o = torch.empty(fr * n, heads * d, device=dev, dtype=torch.float16)
 a = torch.randn(131072, 320, device=dev, dtype=torch.float16)
 w2 = torch.randn(320, 320, device=dev, dtype=torch.float16) * 0.05
@@ -34,7 +32,7 @@ def conv():
 
 def attn():
     ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], fr, n, heads, d, dpad, bank_k=bank[:, :hp],
-                  bank_v=bank[:, hp:], bank_tokens=n, n_banks=1, first_bank_frame=16, frames_per_bank=16, out=o, denom_in_v=True)
+                  bank_v=bank[:, hp:], bank_tokens=n, n_banks=1, first_bank_frame=16, frames_per_bank=16, out=o)
 
 
 def lin():

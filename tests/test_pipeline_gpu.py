@@ -66,3 +66,33 @@ def test_vae_kernel_decode_against_oracle(cuda_dev):
     err = rel_l2(out, ref)
     print(f"vae kernel decode rel-L2 = {err:.3e}")
     assert err < 1e-2
+
+
+def test_pipeline_graph_replay_matches_eager_and_is_repeatable(cuda_dev):
+    """Two overlapping windows, CFG: (a) the cached CUDA-graph session (first video = capture, second = pure replay) and
+    the eager path run the same kernels on the same data and must agree to fp32-accumulation-order noise; (b) a replayed
+    session must not leak state from the previous video (different latents in between)."""
+    gold = torch.load(os.path.join(GOLDEN, "pipeline_small.pt"))
+    P = gold["params"]
+    pipe = build_pipeline(P, cuda_dev)
+    L = 24
+    ref_image, poses, ref_pose = pipeline_inputs(P["size"], L, P["seeds"]["inputs"])
+    shape = (1, 4, L, P["size"] // 8, P["size"] // 8)
+    lat_a = torch.randn(shape, generator=torch.manual_seed(5)).to(torch.float16)
+    lat_b = torch.randn(shape, generator=torch.manual_seed(6)).to(torch.float16)
+    args = (ref_image, poses, ref_pose, P["size"], P["size"], L, 3, P["guidance"])
+
+    def run(lat, graph):
+        pipe.use_cuda_graph = graph
+        v = pipe(*args, latents=lat.clone()).videos
+        return pipe.last_latents.float().cpu(), v
+    a1, va1 = run(lat_a, True)        # builds + captures the session
+    b1, _ = run(lat_b, True)          # replay with other latents
+    a2, va2 = run(lat_a, True)        # replay again with the first latents
+    ae, vae_ = run(lat_a, False)      # eager
+    assert len(pipe._sessions) == 1
+    e_rep, e_eager, e_other = rel_l2(a2, a1), rel_l2(ae, a1), rel_l2(b1, a1)
+    print(f"replay vs first {e_rep:.3e}; eager vs graph {e_eager:.3e}; other latents {e_other:.3e}; "
+          f"video eager vs graph {rel_l2(vae_, va1):.3e}")
+    assert e_other > 1e-1
+    assert e_rep < 1e-3 and e_eager < 1e-3 and rel_l2(va2, va1) < 1e-3 and rel_l2(vae_, va1) < 1e-3
