@@ -10,11 +10,15 @@
 namespace ap {
 
 // ---------------------------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[frame][group] = {sum, sumsq} over (HW x channels-per-group).
-// grid (row_chunks, Nf); block = (C/8) * k threads; thread owns 8 consecutive channels, strides over rows.
+// GroupNorm statistics, deterministic two-stage reduction (no atomics: results are bit-reproducible run to run).
+// Stage 1: grid (row_chunks, Nf); block = (C/8) * k threads; a thread owns 8 consecutive channels and strides over the
+// block's rows; per-thread sums go through shared memory and are combined per group in a fixed order;
+// partials[frame][chunk][group] = {sum, sumsq} (only the groups this source intersects are written).
+// Stage 2 (gn_finalize_kernel): per frame, 8 lanes per group add the chunks' partials of both sources in double and
+// write stats[frame][group] = {mean, rstd}.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int c_off, int cpg, int rows_per_block,
-                                float* __restrict__ stats, int G) {
+                                float2* __restrict__ partials, int G) {
   const int vecs = C >> 3;
   const int k = blockDim.x / vecs;
   const int cv = threadIdx.x % vecs;
@@ -38,33 +42,55 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int
       }
     }
   }
-  extern __shared__ float sg[];  // [G][2]
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sg[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float2 sh[];  // [k][C] per-thread channel sums
   if (rl < k) {
-    // merge the 8 channels into (at most 2..8) groups before touching shared memory
-    int g_prev = (c_off + cv * 8) / cpg;
-    float as = 0.f, aq = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c_off + cv * 8 + j) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&sg[2 * g_prev], as);
-        atomicAdd(&sg[2 * g_prev + 1], aq);
-        as = aq = 0.f;
-        g_prev = g;
-      }
-      as += s[j];
-      aq += q[j];
-    }
-    atomicAdd(&sg[2 * g_prev], as);
-    atomicAdd(&sg[2 * g_prev + 1], aq);
+    for (int j = 0; j < 8; ++j) sh[rl * C + cv * 8 + j] = make_float2(s[j], q[j]);
   }
   __syncthreads();
   const int g_lo = c_off / cpg, g_hi = (c_off + C - 1) / cpg;
   for (int g = g_lo + threadIdx.x; g <= g_hi; g += blockDim.x) {
-    atomicAdd(&stats[((long long)frame * G + g) * 2], sg[2 * g]);
-    atomicAdd(&stats[((long long)frame * G + g) * 2 + 1], sg[2 * g + 1]);
+    const int c0 = max(g * cpg, c_off) - c_off;
+    const int c1 = min((g + 1) * cpg, c_off + C) - c_off;
+    float as = 0.f, aq = 0.f;
+    for (int c = c0; c < c1; ++c)
+      for (int r = 0; r < k; ++r) {
+        const float2 v = sh[r * C + c];
+        as += v.x;
+        aq += v.y;
+      }
+    partials[((long long)frame * gridDim.x + blockIdx.x) * G + g] = make_float2(as, aq);
+  }
+}
+
+// grid Nf, block 8 * G threads. Source i covers groups [glo_i, ghi_i] with chunks_i partials per frame (chunks1 = 0: none).
+__global__ void gn_finalize_kernel(const float2* __restrict__ p0, int chunks0, int glo0, int ghi0,
+                                   const float2* __restrict__ p1, int chunks1, int glo1, int ghi1, int G,
+                                   double inv_count, float eps, float2* __restrict__ stats) {
+  const int frame = blockIdx.x;
+  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  double s = 0.0, q = 0.0;
+  if (g >= glo0 && g <= ghi0)
+    for (int c = sub; c < chunks0; c += 8) {
+      const float2 v = p0[((long long)frame * chunks0 + c) * G + g];
+      s += v.x;
+      q += v.y;
+    }
+  if (chunks1 > 0 && g >= glo1 && g <= ghi1)
+    for (int c = sub; c < chunks1; c += 8) {
+      const float2 v = p1[((long long)frame * chunks1 + c) * G + g];
+      s += v.x;
+      q += v.y;
+    }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (sub == 0) {
+    const double mean = s * inv_count;
+    const double var = fmax(q * inv_count - mean * mean, 0.0);
+    stats[(long long)frame * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
 }
 
@@ -72,8 +98,8 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int
 // [rows, C_total] output (this is also how the skip-concat gets materialised, in normalised form, for free).
 template <bool SILU>
 __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int c_off, int C_total, int cpg,
-                                int rows_per_block, const float* __restrict__ stats, int G, float inv_count,
-                                float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int rows_per_block, const float2* __restrict__ stats, int G,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __half* __restrict__ y) {
   const int vecs = C >> 3;
   const int k = blockDim.x / vecs;
@@ -88,13 +114,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int
   for (int j = 0; j < 8; ++j) {
     const int c = c_off + cv * 8 + j;
     const int g = c / cpg;
-    const float sum = stats[((long long)frame * G + g) * 2];
-    const float sq = stats[((long long)frame * G + g) * 2 + 1];
-    const float mean = sum * inv_count;
-    const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    a[j] = rstd * gamma[c];
-    b[j] = beta[c] - mean * a[j];
+    const float2 mr = stats[(long long)frame * G + g];   // {mean, rstd}
+    a[j] = mr.y * gamma[c];
+    b[j] = beta[c] - mr.x * a[j];
   }
   const __half* src = x + ((long long)frame * HW) * C + cv * 8;
   __half* dst = y + ((long long)frame * HW) * C_total + c_off + cv * 8;
@@ -227,7 +249,7 @@ static void gn_launch_geometry(int HW, int C, int Nf, int* threads, int* rows_pe
   *threads = vecs * k;
   // aim for >= ~4 waves of 148 SMs when the tensor is large, but at least 8 rows per row-lane
   int rpb = 8 * k;
-  while ((long long)((HW + rpb - 1) / rpb) * Nf > 148 * 16 && rpb < HW) rpb *= 2;
+  while ((long long)((HW + rpb - 1) / rpb) * Nf > AP_GN_MAX_BLOCKS && rpb < HW) rpb *= 2;
   *rows_per_block = rpb;
   *chunks = (HW + rpb - 1) / rpb;
 }
@@ -236,7 +258,8 @@ static void gn_launch_geometry(int HW, int C, int Nf, int* threads, int* rows_pe
 
 using namespace ap;
 
-// stats: fp32 [Nf, G, 2] workspace (zeroed here). x2/C2 optional second source (channel concat).
+// stats: fp32 workspace of 2*groups*(Nf + 2*AP_GN_MAX_BLOCKS) floats: [Nf, G] {mean, rstd} followed by the per-block
+// partial sums of the (up to two) sources. x2/C2 optional second source (channel concat).
 extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int HW, int groups,
                                      float eps, const float* gamma, const float* beta, int silu, float* stats,
                                      void* out, void* stream_) {
@@ -246,30 +269,38 @@ extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int 
   AP_REQUIRE(C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
   AP_REQUIRE(C1 % 8 == 0 && (!x2 || C2 % 8 == 0), "groupnorm: channel counts must be multiples of 8");
   AP_REQUIRE(C1 / 8 <= 1024 && (!x2 || C2 / 8 <= 1024), "groupnorm: too many channels");
+  AP_REQUIRE(groups * 8 <= 1024, "groupnorm: at most 128 groups");
   const int cpg = C / groups;
-  AP_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * Nf, stream));
+  const int nsrc = x2 ? 2 : 1;
   const void* srcs[2] = {x, x2};
   const int cs[2] = {C1, C2};
   const int offs[2] = {0, C1};
-  for (int s = 0; s < (x2 ? 2 : 1); ++s) {
-    int threads, rpb, chunks;
-    gn_launch_geometry(HW, cs[s], Nf, &threads, &rpb, &chunks);
-    gn_stats_kernel<<<dim3(chunks, Nf), threads, sizeof(float) * 2 * groups, stream>>>(
-        (const __half*)srcs[s], HW, cs[s], offs[s], cpg, rpb, stats, groups);
+  int threads[2], rpb[2], chunks[2] = {0, 0};
+  float2* stat2 = reinterpret_cast<float2*>(stats);
+  float2* part[2] = {stat2 + (long long)Nf * groups, nullptr};
+  for (int s = 0; s < nsrc; ++s) {
+    gn_launch_geometry(HW, cs[s], Nf, &threads[s], &rpb[s], &chunks[s]);
+    AP_REQUIRE((long long)chunks[s] * Nf <= AP_GN_MAX_BLOCKS, "groupnorm: %d frames exceed the partial-sum workspace", Nf);
+    const int k = threads[s] / (cs[s] / 8);
+    AP_REQUIRE((size_t)k * cs[s] * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too wide for the reduction buffer", cs[s]);
+    if (s == 0) part[1] = part[0] + (long long)Nf * chunks[0] * groups;
+    gn_stats_kernel<<<dim3(chunks[s], Nf), threads[s], sizeof(float2) * k * cs[s], stream>>>(
+        (const __half*)srcs[s], HW, cs[s], offs[s], cpg, rpb[s], part[s], groups);
   }
   AP_CHECK_CUDA(cudaGetLastError());
-  const float inv_count = 1.0f / ((float)HW * (float)cpg);
-  for (int s = 0; s < (x2 ? 2 : 1); ++s) {
-    int threads, rpb, chunks;
-    gn_launch_geometry(HW, cs[s], Nf, &threads, &rpb, &chunks);
+  const double inv_count = 1.0 / ((double)HW * (double)cpg);
+  gn_finalize_kernel<<<Nf, 8 * groups, 0, stream>>>(part[0], chunks[0], 0, (C1 - 1) / cpg, part[1], nsrc == 2 ? chunks[1] : 0,
+                                                   C1 / cpg, (C - 1) / cpg, groups, inv_count, eps, stat2);
+  AP_CHECK_CUDA(cudaGetLastError());
+  for (int s = 0; s < nsrc; ++s) {
     if (silu)
-      gn_apply_kernel<true><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
-                                                                      cpg, rpb, stats, groups, inv_count, eps, gamma,
-                                                                      beta, (__half*)out);
+      gn_apply_kernel<true><<<dim3(chunks[s], Nf), threads[s], 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
+                                                                            cpg, rpb[s], stat2, groups, gamma, beta,
+                                                                            (__half*)out);
     else
-      gn_apply_kernel<false><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
-                                                                       cpg, rpb, stats, groups, inv_count, eps, gamma,
-                                                                       beta, (__half*)out);
+      gn_apply_kernel<false><<<dim3(chunks[s], Nf), threads[s], 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
+                                                                             cpg, rpb[s], stat2, groups, gamma, beta,
+                                                                             (__half*)out);
   }
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;

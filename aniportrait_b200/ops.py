@@ -10,6 +10,7 @@ import torch
 from . import _lib
 from ._lib import I, LL, check, fptr, lib, ptr, stream_ptr
 
+GN_MAX_BLOCKS = 2368  # AP_GN_MAX_BLOCKS in include/aniportrait_b200.h
 KERNEL_LAUNCHES = 0  # incremented by every wrapper; bench.py reports it as gpu_launches
 
 
@@ -131,7 +132,8 @@ def _stats_workspace(device, n):
     key = (device.index, torch.cuda.current_stream().cuda_stream)
     buf = _stats_ws.get(key)
     if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n, 4096), dtype=torch.float32, device=device)
+        # sized once for any realistic frame count: CUDA graphs keep this pointer, so it must never be re-allocated
+        buf = torch.empty(max(n, 2 * 32 * (4096 + 2 * GN_MAX_BLOCKS)), dtype=torch.float32, device=device)
         _stats_ws[key] = buf
     return buf
 
@@ -151,7 +153,7 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     assert gamma.dtype == torch.float32 and gamma.numel() == c and beta.numel() == c
     if out is None:
         out = torch.empty(*x.shape[:-1], c, dtype=torch.float16, device=x.device)
-    stats = _stats_workspace(x.device, 2 * groups * nf)
+    stats = _stats_workspace(x.device, 2 * groups * (nf + 2 * GN_MAX_BLOCKS))
     rc = lib().ap_groupnorm_nhwc_f16(ptr(x), I(c1), ptr(x2), I(c2), I(nf), I(hw), I(groups), _lib.c_float(eps),
                                      fptr(gamma), fptr(beta), I(1 if silu else 0), fptr(stats), ptr(out),
                                      stream_ptr())

@@ -68,8 +68,10 @@ int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, i
  * Replaces InflatedGroupNorm / nn.GroupNorm (reference src/models/resnet.py:21-29,221-222,232-238;
  * src/models/transformer_3d.py:124; src/models/motion_module.py:156; src/models/unet_3d.py:573-574).
  * x: [Nf, HW, C1], x2: [Nf, HW, C2] or NULL, out: [Nf, HW, C1+C2]; statistics per (frame, group) in fp32.
- * stats: caller-provided fp32 workspace of 2*groups*Nf floats.
+ * stats: caller-provided fp32 workspace of 2*groups*(Nf + 2*AP_GN_MAX_BLOCKS) floats ({mean, rstd} per (frame, group)
+ * followed by per-block partial sums: the reduction is atomic-free, results are bit-reproducible run to run).
  */
+#define AP_GN_MAX_BLOCKS 2368
 int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int HW, int groups, float eps,
                           const float* gamma, const float* beta, int silu, float* stats, void* out, void* stream);
 

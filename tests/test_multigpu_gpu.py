@@ -69,6 +69,7 @@ def test_window_sharding_two_gpus_nccl():
     e_lat = rel_l2(sh0_lat, single_lat)
     e_vid = rel_l2(sh0, single)
     print(f"2-GPU window sharding vs single process: latents {e_lat:.3e}, video {e_vid:.3e}")
-    # same kernels, same per-window results; only the fp32 accumulation order across ranks differs
-    assert e_lat < 1e-3 and e_vid < 1e-3
-    assert clip_err0 < 1e-3 and clip_err1 < 1e-3
+    # same kernels, same per-window results; each accumulator element receives at most one contribution per rank, so the
+    # NCCL sum is exact as well
+    assert e_lat < 1e-6 and e_vid < 1e-6
+    assert clip_err0 < 1e-6 and clip_err1 < 1e-6
