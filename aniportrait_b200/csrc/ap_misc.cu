@@ -1,4 +1,6 @@
 // Temporal (frame-axis) attention core and small HBM-bound elementwise / layout kernels of the hot path.
+#include <stdlib.h>
+
 #include "ap_host.h"
 
 namespace ap {
@@ -135,6 +137,174 @@ temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __res
       }
     }
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Temporal attention, F <= 16, head_dim D in {40, 80, 160}: the path every UNet call takes (F = 16 window).
+// A block owns one (batch, position) and a group of HG = 320 / D heads, i.e. 320 channels of q, k and v of the F token
+// rows (b*F + f)*N + p. The rows are fetched with fully coalesced 16-byte cp.async (each row contributes three contiguous
+// 640-byte segments) into a padded shared tile (row stride 1936 B: conflict-free ldmatrix); one warp per head then does
+// S = Q.K^T and O = P.V with mma.sync m16n8k16 (the 16 frames are exactly one MMA tile), the softmax lives in the
+// accumulator registers, O goes back through shared memory (over the head's dead Q columns) and leaves as coalesced
+// 640-byte row segments. The previous kernel (kept below for F > 16 / other head sizes) let every lane walk its own token
+// row: 32 cache lines per load instruction and ~1.3 G scalar FMAs made it 3x slower than the HBM time of its operands.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_1688(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+constexpr int TA_GC = 320;            // channels of q (and of k, v) per block
+constexpr int TA_RS = 3 * TA_GC + 8;  // padded shared row stride in halves (1936 B)
+
+template <int D>
+__global__ void __launch_bounds__(32 * (TA_GC / D))
+temporal_attn_mma_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int F,
+                         int N, int C, float scale_log2) {
+  constexpr int HG = TA_GC / D;        // heads (= warps) per block
+  constexpr int NT = 32 * HG;
+  constexpr int SEG_V = TA_GC / 8;     // uint4 per 640-byte segment
+  __shared__ __align__(16) __half tile[16 * TA_RS];
+  const int groups = C / TA_GC;
+  const int hg = blockIdx.x % groups;
+  const long long bp = blockIdx.x / groups;      // b * N + p
+  const int b = (int)(bp / N), p = (int)(bp % N);
+  const long long row0 = (long long)b * F * N + p;   // token row of frame f: row0 + f * N
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+
+  // ---- coalesced fetch: F rows x 3 segments (q | k | v) x 40 x 16 B
+  for (int idx = threadIdx.x; idx < F * 3 * SEG_V; idx += NT) {
+    const int f = idx / (3 * SEG_V), c = idx % (3 * SEG_V);
+    const int seg = c / SEG_V, within = c % SEG_V;
+    const __half* src = qkv + (row0 + (long long)f * N) * ld + seg * C + hg * TA_GC + within * 8;
+    const uint32_t dst = tile_s + (uint32_t)(f * TA_RS + c * 8) * 2;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  }
+  if (F < 16) {   // unused frame rows must read as zeros (they enter the MMAs as K / V rows)
+    for (int idx = threadIdx.x; idx < (16 - F) * 3 * SEG_V; idx += NT) {
+      const int f = F + idx / (3 * SEG_V), c = idx % (3 * SEG_V);
+      *reinterpret_cast<uint4*>(tile + f * TA_RS + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int g = l >> 2, q4 = l & 3;
+  const int j8 = l >> 3, r8 = l & 7;
+  const uint32_t q_s = tile_s + (uint32_t)(w * D) * 2;
+  const uint32_t k_s = q_s + TA_GC * 2;
+  const uint32_t v_s = k_s + TA_GC * 2;
+
+  // ---- S = Q K^T   (16 x 16 per head): two n-tiles of 8 key frames
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    ldsm_x4(q_s + (uint32_t)((((j8 & 1) * 8 + r8) * TA_RS) + ks * 16 + (j8 >> 1) * 8) * 2, a0, a1, a2, a3);
+    ldsm_x4(k_s + (uint32_t)((((j8 >> 1) * 8 + r8) * TA_RS) + ks * 16 + (j8 & 1) * 8) * 2, b0, b1, b2, b3);
+    mma_16816(s0, a0, a1, a2, a3, b0, b1);
+    mma_16816(s1, a0, a1, a2, a3, b2, b3);
+  }
+  if (D % 16 == 8) {   // d = 40: 8-channel tail
+    constexpr int c0 = (D / 16) * 16;
+    uint32_t a0, a1, b0, b1;
+    const int jj = j8 & 1;   // lanes 16-31 mirror 0-15 (their addresses are ignored by .x2)
+    ldsm_x2(q_s + (uint32_t)((jj * 8 + r8) * TA_RS + c0) * 2, a0, a1);
+    ldsm_x2(k_s + (uint32_t)((jj * 8 + r8) * TA_RS + c0) * 2, b0, b1);
+    mma_1688(s0, a0, a1, b0);
+    mma_1688(s1, a0, a1, b1);
+  }
+  // ---- softmax over the key frames: rows g (c0,c1) and g+8 (c2,c3); columns nt*8 + 2*q4 + {0,1}
+  const int col = 2 * q4;
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (col + e >= F) { s0[e] = -INFINITY; s0[2 + e] = -INFINITY; }
+    if (8 + col + e >= F) { s1[e] = -INFINITY; s1[2 + e] = -INFINITY; }
+    mx_lo = fmaxf(mx_lo, fmaxf(s0[e], s1[e]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s0[2 + e], s1[2 + e]));
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, o));
+  }
+  float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    s0[e] = exp2f((s0[e] - mx_lo) * scale_log2);
+    s1[e] = exp2f((s1[e] - mx_lo) * scale_log2);
+    s0[2 + e] = exp2f((s0[2 + e] - mx_hi) * scale_log2);
+    s1[2 + e] = exp2f((s1[2 + e] - mx_hi) * scale_log2);
+    l_lo += s0[e] + s1[e];
+    l_hi += s0[2 + e] + s1[2 + e];
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, o);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, o);
+  }
+  const float il = 1.f / l_lo, ih = 1.f / l_hi;
+  const uint32_t pa0 = pack_h2(s0[0] * il, s0[1] * il), pa1 = pack_h2(s0[2] * ih, s0[3] * ih);
+  const uint32_t pa2 = pack_h2(s1[0] * il, s1[1] * il), pa3 = pack_h2(s1[2] * ih, s1[3] * ih);
+
+  // ---- O = P V   (16 x D per head), channel n-tiles of 8, two per ldmatrix.x4.trans
+  __half* o_row_lo = tile + g * TA_RS + w * D + col;          // O overwrites this head's (dead) Q columns
+  __half* o_row_hi = o_row_lo + 8 * TA_RS;
+#pragma unroll
+  for (int np = 0; np < D / 16; ++np) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4_t(v_s + (uint32_t)((((j8 & 1) * 8 + r8) * TA_RS) + (np * 2 + (j8 >> 1)) * 8) * 2, b0, b1, b2, b3);
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816(o0, pa0, pa1, pa2, pa3, b0, b1);
+    mma_16816(o1, pa0, pa1, pa2, pa3, b2, b3);
+    *reinterpret_cast<uint32_t*>(o_row_lo + np * 16) = pack_h2(o0[0], o0[1]);
+    *reinterpret_cast<uint32_t*>(o_row_hi + np * 16) = pack_h2(o0[2], o0[3]);
+    *reinterpret_cast<uint32_t*>(o_row_lo + np * 16 + 8) = pack_h2(o1[0], o1[1]);
+    *reinterpret_cast<uint32_t*>(o_row_hi + np * 16 + 8) = pack_h2(o1[2], o1[3]);
+  }
+  if (D % 16 == 8) {
+    constexpr int c0 = (D / 16) * 16;
+    uint32_t b0, b1;
+    ldsm_x2_t(v_s + (uint32_t)((((j8 & 1) * 8 + r8) * TA_RS) + c0) * 2, b0, b1);
+    float o0[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816(o0, pa0, pa1, pa2, pa3, b0, b1);
+    *reinterpret_cast<uint32_t*>(o_row_lo + c0) = pack_h2(o0[0], o0[1]);
+    *reinterpret_cast<uint32_t*>(o_row_hi + c0) = pack_h2(o0[2], o0[3]);
+  }
+  __syncthreads();
+  // ---- coalesced store: F rows x 640 B
+  for (int idx = threadIdx.x; idx < F * SEG_V; idx += NT) {
+    const int f = idx / SEG_V, c = idx % SEG_V;
+    *reinterpret_cast<uint4*>(out + (row0 + (long long)f * N) * ldo + hg * TA_GC + c * 8) =
+        *reinterpret_cast<const uint4*>(tile + f * TA_RS + c * 8);
   }
 }
 
@@ -327,6 +497,16 @@ extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* ou
   AP_REQUIRE(heads >= 1 && heads <= 8 && C % heads == 0, "temporal_attention: heads=%d unsupported", heads);
   const int d = C / heads;
   AP_REQUIRE(d % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "temporal_attention: head_dim/ld must be multiples of 8");
+  static const bool force_scalar = getenv("AP_TEMPORAL_SCALAR") != nullptr;   // A/B switch: the pre-MMA kernel
+  if (!force_scalar && F <= 16 && C % TA_GC == 0 && heads * d == C && (d == 40 || d == 80 || d == 160)) {
+    const unsigned grid = (unsigned)((long long)B * N * (C / TA_GC));
+    const float sl2 = scale * 1.4426950408889634f;
+    if (d == 40) temporal_attn_mma_kernel<40><<<grid, 256, 0, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
+    else if (d == 80) temporal_attn_mma_kernel<80><<<grid, 128, 0, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
+    else temporal_attn_mma_kernel<160><<<grid, 64, 0, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
+    AP_CHECK_CUDA(cudaGetLastError());
+    return AP_OK;
+  }
   int VEC = 1;
   for (int v : {5, 4, 2, 1})
     if (d % (8 * v) == 0) { VEC = v; break; }

@@ -31,6 +31,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (rl < k) {
     const __half* base = x + ((long long)frame * HW) * C + cv * 8;
+#pragma unroll 4
     for (int r = r0 + rl; r < r1; r += k) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * C));
       const __half2* h2 = reinterpret_cast<const __half2*>(&u);
@@ -120,6 +121,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int
   }
   const __half* src = x + ((long long)frame * HW) * C + cv * 8;
   __half* dst = y + ((long long)frame * HW) * C_total + c_off + cv * 8;
+#pragma unroll 4
   for (int r = r0 + rl; r < r1; r += k) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * C));
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);

@@ -10,6 +10,7 @@ import torch
 from . import _lib
 from ._lib import I, LL, check, fptr, lib, ptr, stream_ptr
 
+SHAPE_LOG = None  # dev aid: set to a list to record (kind, M, N, K, flags) of every GEMM / conv launch
 GN_MAX_BLOCKS = 2368  # AP_GN_MAX_BLOCKS in include/aniportrait_b200.h
 KERNEL_LAUNCHES = 0  # incremented by every wrapper; bench.py reports it as gpu_launches
 
@@ -88,6 +89,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
                            LL(residual.stride(0) if residual is not None else 0), ptr(out), LL(out.stride(0)),
                            I(nout), I((1 if geglu else 0) | (2 if out_f32 else 0)), I(block_n), stream_ptr())
     check(rc, "ap_gemm_f16")
+    if SHAPE_LOG is not None:
+        SHAPE_LOG.append(("gemm_geglu" if geglu else "gemm", M, N, K1 + K2, int(residual is not None)))
     _count()
     return out
 
@@ -118,6 +121,8 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, cout: int, bias: torch.Tens
                                    I(cout_p), fptr(bias), LL(bias_group_rows), ptr(residual), ptr(out), LL(cout),
                                    I(cout), I(block_n), stream_ptr())
     check(rc, "ap_conv3x3_nhwc_f16")
+    if SHAPE_LOG is not None:
+        SHAPE_LOG.append((f"conv3x3_s{stride}", nf * ho * wo, cout_p, 9 * (c1 + c2), int(residual is not None)))
     _count()
     return out
 

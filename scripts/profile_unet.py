@@ -31,8 +31,13 @@ with torch.no_grad():
     for _ in range(2):
         unet3d.forward_nhwc(x, 2, F, tt, ehs, pose)
     torch.cuda.synchronize()
+    if os.environ.get("AP_SHAPE_LOG"):
+        import json
+        ops.SHAPE_LOG = []
     torch.cuda.profiler.start()
     unet3d.forward_nhwc(x, 2, F, tt, ehs, pose)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+    if ops.SHAPE_LOG is not None:
+        json.dump(ops.SHAPE_LOG, open(os.environ["AP_SHAPE_LOG"], "w"))
 print("done")
