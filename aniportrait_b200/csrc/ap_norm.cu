@@ -5,6 +5,8 @@
 // src/models/transformer_3d.py:58-60,124; src/models/motion_module.py:119-121,156; src/models/unet_3d.py:238-249,573-574)
 // and nn.LayerNorm (+ temporal positional-encoding add) (src/models/attention.py:331-362;
 // src/models/motion_module.py:228-241,262-277,365-366).
+#include <stdlib.h>
+
 #include "ap_host.h"
 
 namespace ap {
@@ -95,6 +97,15 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ p0, int chunks0, i
   }
 }
 
+// x * sigmoid(x) with two MUFU ops (ex2, rcp) and no IEEE-division sequence: the SiLU variant of gn_apply was ALU-bound
+// (47 us against 25 us without SiLU at 32 x 4096 x 320), not HBM-bound. Relative error ~2^-22, far below fp16 resolution.
+__device__ __forceinline__ float silu_fast(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return v * r;
+}
+
 // Apply: y = (x - mean) * rstd * gamma + beta  (optionally SiLU), written at channel offset c_off of an
 // [rows, C_total] output (this is also how the skip-concat gets materialised, in normalised form, for free).
 template <bool SILU>
@@ -133,8 +144,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int
       float v0 = f.x * a[2 * j] + b[2 * j];
       float v1 = f.y * a[2 * j + 1] + b[2 * j + 1];
       if (SILU) {
-        v0 = v0 / (1.f + __expf(-v0));
-        v1 = v1 / (1.f + __expf(-v1));
+        v0 = silu_fast(v0);
+        v1 = silu_fast(v1);
       }
       o2[j] = __floats2half2_rn(v0, v1);
     }
@@ -201,6 +212,85 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long rows, i
       dst[idx] = __floats2half2_rn(o0, o1);
     }
   }
+}
+
+// LayerNorm, wide-load variant for C % 64 == 0: 8 lanes per row (4 rows per warp), each lane keeps C/64 16-byte vectors of
+// its row in registers, so every load / store instruction moves 4 x 128 contiguous bytes (the one-warp-per-row kernel
+// above issues 4-byte accesses and reached 3.8 TB/s on 131072 x 320). Same exact two-pass statistics.
+template <int MAXV>  // MAXV >= C / 64
+__global__ void __launch_bounds__(256)
+layernorm8_kernel(const __half* __restrict__ x, long long rows, int C, float eps, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const float* __restrict__ pe, int rows_per_pe, int pe_period,
+                  __half* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const bool ok = row < rows;
+  const int nv = C >> 6;   // 16-byte vectors per lane
+  const uint4* src = reinterpret_cast<const uint4*>(x + (ok ? row : 0) * C);
+  uint4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) v[i] = ok ? __ldg(src + sub + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h[t]);
+        sum += f.x + f.y;
+      }
+    }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h[t]);
+        const float dx = f.x - mean, dy = f.y - mean;
+        sq += dx * dx + dy * dy;
+      }
+    }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  if (!ok) return;
+  const float* pe_row = pe ? pe + (long long)((row / rows_per_pe) % pe_period) * C : nullptr;
+  uint4* dst = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c0 = (sub + 8 * i) * 8;
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h[t]);
+        o[2 * t] = (f.x - mean) * rstd * gg[2 * t] + bb[2 * t];
+        o[2 * t + 1] = (f.y - mean) * rstd * gg[2 * t + 1] + bb[2 * t + 1];
+      }
+      if (pe_row) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe_row + c0)), p1 = __ldg(reinterpret_cast<const float4*>(pe_row + c0 + 4));
+        o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w;
+        o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
+      }
+      uint4 u;
+      __half2* oh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(o[2 * t], o[2 * t + 1]);
+      dst[sub + 8 * i] = u;
+    }
 }
 
 // Row softmax (fp16 in/out, fp32 math) for the VAE's single-head 4096-token attention, which is evaluated as
@@ -323,6 +413,20 @@ extern "C" int ap_layernorm_f16(const void* x, long long rows, int C, float eps,
   AP_REQUIRE(C % 2 == 0 && C <= 64 * 32, "layernorm: C=%d unsupported (even, <= 2048)", C);
   AP_REQUIRE(pe == nullptr || (rows_per_pe > 0 && pe_period > 0), "layernorm: bad pe geometry");
   const int wpb = 8;
+  if (C % 64 == 0 && C / 64 <= 22 && getenv("AP_LAYERNORM_NARROW") == nullptr) {
+    const unsigned grid8 = (unsigned)((rows + 4 * wpb - 1) / (4 * wpb));
+    const int nv = C / 64;
+#define AP_LN8(MV)                                                                                                       \
+  layernorm8_kernel<MV><<<grid8, wpb * 32, 0, stream>>>((const __half*)x, rows, C, eps, gamma, beta, pe,                  \
+                                                        rows_per_pe > 0 ? rows_per_pe : 1, pe_period > 0 ? pe_period : 1, \
+                                                        (__half*)out)
+    if (nv <= 5) AP_LN8(5);
+    else if (nv <= 10) AP_LN8(10);
+    else AP_LN8(22);
+#undef AP_LN8
+    AP_CHECK_CUDA(cudaGetLastError());
+    return AP_OK;
+  }
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const int maxv = (C / 2 + 31) / 32;
 #define AP_LN(MV)                                                                                              \

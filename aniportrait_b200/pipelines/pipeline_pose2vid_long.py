@@ -449,7 +449,7 @@ class Pose2VideoPipeline:
                  callback: Optional[Callable[[int, int, torch.Tensor], None]] = None,
                  callback_steps: Optional[int] = 1, context_schedule="uniform", context_frames=16, context_stride=1,
                  context_overlap=4, context_batch_size=1, interpolation_factor=1, clip_image_embeds=None,
-                 latents=None, dist_mode=None, **kwargs):
+                 latents=None, dist_mode=None, clip_resize=True, **kwargs):
         """Reference signature (pipeline_pose2vid_long.py:338-363). Host-side preprocessing, then run_device(), then the
         fp32 host copy of the video.
         dist_mode (only with torch.distributed initialised):
@@ -470,8 +470,10 @@ class Pose2VideoPipeline:
             raise RuntimeError("aniportrait_b200.Pose2VideoPipeline runs on CUDA (sm_100a) only: no CPU fallback")
         clip_pixels = None
         if clip_image_embeds is None:
-            clip_pixels = self.clip_image_processor.preprocess(ref_image.resize((224, 224)),
-                                                               return_tensors="pt").pixel_values
+            # the long pipeline squashes the portrait to 224x224 first (reference :375-377); the short one lets the CLIP
+            # processor resize + centre-crop (src/pipelines/pipeline_pose2vid.py:320-322)
+            clip_src = ref_image.resize((224, 224)) if clip_resize else ref_image
+            clip_pixels = self.clip_image_processor.preprocess(clip_src, return_tensors="pt").pixel_values
         embed_dtype = self.image_encoder.dtype if isinstance(self.image_encoder, torch.nn.Module) else torch.float16
         latents = self.prepare_latents(num_images_per_prompt, self.denoising_unet.in_channels, width, height,
                                        video_length, embed_dtype, device, generator, latents)

@@ -343,11 +343,13 @@ def context_windows(num_frames, size=16, overlap=4):
 
 
 def denoise_loop(sd_unet, sd_ref, sd_pose, latents, ref_latents, clip_embed, pose_cond, steps, guidance=3.5,
-                 context_frames=16, context_overlap=4):
+                 context_frames=16, context_overlap=4, c=SD15):
     """Pose2VideoPipeline.__call__ denoising loop (src/pipelines/pipeline_pose2vid_long.py:459-567), CFG on.
-    latents [1,4,L,h,w]; ref_latents [1,4,h,w]; clip_embed [1,768]; pose_cond [1,3,L,H,W] (already preprocessed)."""
+    latents [1,4,L,h,w]; ref_latents [1,4,h,w]; clip_embed [1,768]; pose_cond [1,3,L,H,W] (already preprocessed).
+    With context_frames >= L this is also the single-window loop of src/pipelines/pipeline_pose2vid.py:396-437 (one
+    PoseGuider pass, one UNet call per step over all frames). `c`: UNet config (block widths) for reduced-size tests."""
     ehs = torch.cat([torch.zeros_like(clip_embed), clip_embed], 0).unsqueeze(1)
-    banks = reference_unet_banks(sd_ref, ref_latents.repeat(2, 1, 1, 1), ehs)
+    banks = reference_unet_banks(sd_ref, ref_latents.repeat(2, 1, 1, 1), ehs, c=c)
     sched = DDIM()
     L = latents.shape[2]
     windows = context_windows(L, context_frames, context_overlap)
@@ -356,8 +358,9 @@ def denoise_loop(sd_unet, sd_ref, sd_pose, latents, ref_latents, clip_embed, pos
         counter = torch.zeros(1, 1, L, 1, 1, dtype=latents.dtype)
         for wdw in windows:
             lat = latents[:, :, wdw].repeat(2, 1, 1, 1, 1)
-            pose_fea = pose_guider_forward(sd_pose, pose_cond[:, :, wdw].repeat(2, 1, 1, 1, 1))
-            pred = unet3d_forward(sd_unet, lat, t, ehs, pose_fea, banks, cfg=True)
+            pose_fea = pose_guider_forward(sd_pose, pose_cond[:, :, wdw].repeat(2, 1, 1, 1, 1),
+                                           c0=c["block_out_channels"][0])
+            pred = unet3d_forward(sd_unet, lat, t, ehs, pose_fea, banks, cfg=True, c=c)
             noise[:, :, wdw] += pred
             counter[:, :, wdw] += 1
         u, cnd = (noise / counter).chunk(2)

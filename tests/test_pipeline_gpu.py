@@ -97,3 +97,56 @@ def test_pipeline_graph_replay_matches_eager_and_is_repeatable(cuda_dev):
           f"video eager vs graph {rel_l2(vae_, va1):.3e}")
     assert e_other > 1e-1
     assert e_rep < 1e-6 and e_eager < 1e-6 and rel_l2(va2, va1) < 1e-6 and rel_l2(vae_, va1) < 1e-6
+
+
+def _host_sd(module):
+    return {k: v.detach().float().cpu() for k, v in module.state_dict().items()}
+
+
+def test_pose2vid_single_window_pipeline_vs_oracle(cuda_dev):
+    """src/pipelines/pipeline_pose2vid.py semantics: all 20 frames are ONE window (temporal attention over 20 frames, no
+    overlap averaging). Final latents vs the CPU oracle's loop with context_frames = L on the same (fp16-rounded) weights,
+    CLIP embedding and reference latents."""
+    from aniportrait_b200.pipelines.pipeline_pose2vid import Pose2VideoPipeline as ShortPipeline
+    from oracle import functional as OF
+    gold = torch.load(os.path.join(GOLDEN, "pipeline_small.pt"))
+    P = gold["params"]
+    base = build_pipeline(P, cuda_dev)
+    pipe = ShortPipeline(vae=base.vae, image_encoder=base.image_encoder, reference_unet=base.reference_unet,
+                         denoising_unet=base.denoising_unet, pose_guider=base.pose_guider, scheduler=base.scheduler)
+    L, steps, size = 20, 2, P["size"]
+    ref_image, poses, ref_pose = pipeline_inputs(size, L, 321)
+    lat0 = torch.randn((1, 4, L, size // 8, size // 8), generator=torch.manual_seed(9)).to(torch.float16)
+    out = pipe(ref_image, poses, ref_pose, size, size, L, steps, P["guidance"], latents=lat0.clone())
+    assert out.videos.shape == (1, 3, L, size, size)
+    got = pipe.last_latents.float().cpu()
+    # oracle inputs produced by the same library modules (CLIP, VAE encoder) on the device
+    with torch.no_grad():
+        clip_px = pipe.clip_image_processor.preprocess(ref_image, return_tensors="pt").pixel_values
+        clip_embed = pipe.image_encoder(clip_px.to(cuda_dev, torch.float16)).image_embeds.float().cpu()
+        ref_t = pipe.ref_image_processor.preprocess(ref_image, height=size, width=size)
+        ref_lat = (pipe.vae.encode(ref_t.to(cuda_dev, torch.float16)).latent_dist.mean * 0.18215).float().cpu()
+        pose_cond = torch.cat([pipe.cond_image_processor.preprocess(p, height=size, width=size) for p in poses], 0)
+        pose_cond = pose_cond.permute(1, 0, 2, 3).unsqueeze(0).to(torch.float16).float()     # [1, 3, L, H, W]
+        cfg = dict(OF.SD15, block_out_channels=tuple(P["chans"]))
+        ref = OF.denoise_loop(_host_sd(pipe.denoising_unet), _host_sd(pipe.reference_unet), _host_sd(pipe.pose_guider),
+                              lat0.float(), ref_lat, clip_embed, pose_cond, steps, guidance=P["guidance"],
+                              context_frames=L, context_overlap=0, c=cfg)
+    err = rel_l2(got, ref)
+    print(f"single-window pipeline (L=20) vs oracle: rel-L2 = {err:.3e}")
+    assert err < 1e-2
+
+
+def test_pose2img_pipeline_matches_one_frame_clip(cuda_dev):
+    from aniportrait_b200.pipelines.pipeline_pose2img import Pose2ImagePipeline
+    gold = torch.load(os.path.join(GOLDEN, "pipeline_small.pt"))
+    P = gold["params"]
+    base = build_pipeline(P, cuda_dev)
+    pipe = Pose2ImagePipeline(vae=base.vae, image_encoder=base.image_encoder, reference_unet=base.reference_unet,
+                              denoising_unet=base.denoising_unet, pose_guider=base.pose_guider, scheduler=base.scheduler)
+    size = P["size"]
+    ref_image, poses, ref_pose = pipeline_inputs(size, 1, 77)
+    img = pipe(ref_image, poses[0], ref_pose, size, size, 2, P["guidance"], generator=torch.manual_seed(3)).images
+    vid = base(ref_image, poses, ref_pose, size, size, 1, 2, P["guidance"], generator=torch.manual_seed(3)).videos
+    assert img.shape == (1, 3, 1, size, size) and torch.isfinite(img).all()
+    assert rel_l2(img, vid) < 1e-6
