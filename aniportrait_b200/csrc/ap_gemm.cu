@@ -51,7 +51,8 @@ struct GemmParams {
   // TMA epilogue (per-warp 32-row x 32-column boxes staged in 64B-swizzled shared memory)
   int tma_epi;             // 1: outputs leave through TMA stores, the residual arrives through TMA loads
   int sub_w, sub_h, sub_n; // conv modes: geometry of a warp's 32-row sub-box
-  int debug;               // AP_GEMM_DEBUG: 1 = skip TMA loads (MMA pace), 2 = skip MMAs (TMA pace); results are garbage
+  int debug;               // AP_GEMM_DEBUG: 1 = skip TMA loads (MMA pace), 2 = skip MMAs (TMA pace), 3 / 4 = skip every other
+                           // B / A load (traffic sensitivity); results are garbage
 };
 
 template <int BN, int CG = 1>
@@ -171,13 +172,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               if (CG == 1 || cta_rank == 0) mbar_arrive(&full_bar[stage]);
             } else {
             // CG == 2: only the leader arms its barrier, with the bytes of BOTH CTAs (their TMA loads signal it)
-            if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
+            // debug 3 / 4 (timing experiments, garbage results): odd k-blocks skip the B / the A load, i.e. 19 % / 31 % less
+            // L2 -> shared-memory traffic at an unchanged MMA schedule
+            const bool load_a = !(p.debug == 4 && (kb & 1)), load_b = !(p.debug == 3 && (kb & 1));
+            if (CG == 1 || cta_rank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], CG * ((load_a ? Cfg::A_BYTES : 0) + (load_b ? Cfg::B_BYTES : 0)));
             void* a_dst = smem_a + stage * Cfg::A_BYTES;
             void* b_dst = smem_b + stage * Cfg::B_BYTES;
             const bool second = within >= p.kb_src1;
             const CUtensorMap* am = second ? &tmA2 : &tmA1;
             const int c0 = (second ? within - p.kb_src1 : within) * Cfg::BK;
-            if (p.a_mode == A_GEMM) {
+            if (!load_a) {
+            } else if (p.a_mode == A_GEMM) {
               if (CG == 2) tma_load_2d_2sm(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
               else tma_load_2d(am, &full_bar[stage], a_dst, c0, m_tile * Cfg::BM);
             } else if (p.a_mode == A_CONV_S1) {
@@ -190,7 +196,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               if (CG == 2) tma_load_5d_2sm(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
               else tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
             }
-            if (CG == 2)
+            if (!load_b) {
+            } else if (CG == 2)
               tma_load_2d_2sm(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN + (int)cta_rank * (BN / 2));
             else
               tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
