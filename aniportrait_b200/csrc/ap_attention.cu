@@ -830,7 +830,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // ------------------------------------------------------------------------ MMA issuer (warp-uniform loop, one
       // elected lane issues: keeps descriptor / stage arithmetic in uniform registers)
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);
+      // the zero padding of the head dimension is not multiplied: Q.K^T stops after ceil(d/16) k-steps and P.V only
+      // produces the first 16*ceil(d/16) output columns (d = 80 in a 128-wide slot: 5 of 8 k-steps, N = 80)
+      const int k_steps = (p.head_dim + 15) >> 4;
+      const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)k_steps * 16, 0, 1);
       uint32_t g = 0, uc = 0;
       auto issue_qk = [&](int t, uint32_t gi, bool release_q) {
         const int stage = gi % ST;
@@ -842,9 +845,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < DPAD / 16; ++kk) {
-            const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
-            const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
-            umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
+            if (kk < k_steps) {
+              const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
+              const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
+              umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
+            }
           }
           umma_commit(&s_full[t]);
           if (release_q) umma_commit(q_empty);
@@ -1477,7 +1482,9 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------- MMA issuer (warp-uniform, elected lane)
     constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);
+    // d = 40 in a 64-wide slot: the zero padding is not multiplied (3 of 4 k-steps for Q.K^T, N = 48 for P.V)
+    const int k_steps = (p.head_dim + 15) >> 4;
+    const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)k_steps * 16, 0, 1);
     const uint32_t qa = smem_u32(smem_q);
     uint32_t g = 0, uc = 0;
     auto issue_qk = [&](uint32_t gi, bool last_of_unit) {
@@ -1489,7 +1496,8 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < DPAD / 16; ++kk)
-          umma_f16_ss(d_tmem, umma_desc_k_sw128(qa + kk * 32), umma_desc_k_sw128(ka + kk * 32), idesc_qk, kk != 0);
+          if (kk < k_steps)
+            umma_f16_ss(d_tmem, umma_desc_k_sw128(qa + kk * 32), umma_desc_k_sw128(ka + kk * 32), idesc_qk, kk != 0);
         umma_commit(&s_full[gi & 1]);
         if (last_of_unit) umma_commit(q_empty);
       }
