@@ -53,21 +53,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// exp2 on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error ~1e-4, i.e. below the
-// fp16 rounding applied to P right after). The MUFU pipe issues only a few ex2 per clock per SM, which makes
-// 128x128x(d=40) attention tiles exp-bound; evaluating a fixed fraction of the exponentials this way (FlashAttention-4's
-// trick) balances the two pipes.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.0f);
-  const float magic = 12582912.0f;                 // 1.5 * 2^23: x + magic rounds x to the nearest integer
-  const float xr = x + magic;
-  const float f = x - (xr - magic);                // f in [-0.5, 0.5]
-  float pfrac = fmaf(0.05515501f, f, 0.24262067f);   // degree-3 minimax of 2^f on [-0.5, 0.5]: max rel err 7.6e-5
-  pfrac = fmaf(pfrac, f, 0.69325914f);
-  pfrac = fmaf(pfrac, f, 0.99992645f);
-  return __int_as_float(__float_as_int(pfrac) + (__float_as_int(xr) << 23));
-}
-
 struct AttnParams {
   int n_frames, tokens, heads, head_dim;
   int bank_tokens;        // 0 = no bank
@@ -385,324 +370,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 
 // ============================================================================================================
-// v2: two 128-query tiles per CTA (FA4-style ping-pong). 10 warps (320 threads -> 204 registers per thread):
-//   warp 0 TMA producer, warp 1 MMA issuer
-//   warps 2-5: softmax + epilogue of query tile A (rows 0..127)
-//   warps 6-9: softmax + epilogue of query tile B (rows 128..255)
-// While WG1 exponentiates S_A(j) the tensor core produces S_B(j) / consumes P_B(j-1), and every SMSP hosts one warp of
-// each tile, so TMEM-load / barrier / MUFU latencies of one tile are hidden behind the other's arithmetic. One S buffer
-// per tile (TMEM cols [0,128) and [128,256)), O_A / O_B behind them (256 + 2*DPAD <= 512 -> DPAD <= 128), K/V ring
-// shared by both tiles.
-// ============================================================================================================
-template <int DPAD, int BN>
-struct Attn2Cfg {
-  static constexpr int SLABS = DPAD / 64;
-  static constexpr int QT_BYTES = 128 * DPAD * 2;          // one query tile
-  static constexpr int Q_BYTES = 2 * QT_BYTES;
-  static constexpr int K_BYTES = BN * DPAD * 2;
-  static constexpr int PT_BYTES = 128 * BN * 2;             // one P tile
-  static constexpr int P_BYTES = 2 * PT_BYTES;
-  static constexpr int KV_STAGE = 2 * K_BYTES;
-  static constexpr int BUDGET = 227 * 1024 - 2048 - Q_BYTES - P_BYTES;
-  static constexpr int STAGES_RAW = BUDGET / KV_STAGE;
-  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + STAGES * KV_STAGE + 1024 + 256;
-  static constexpr uint32_t TMEM_S = 0 /* + t*128 */, TMEM_O = 256 /* + t*DPAD */;
-  static_assert(STAGES >= 2, "need at least a double-buffered K/V ring");
-  static_assert(DPAD % 64 == 0 && DPAD <= 128 && (BN == 64 || BN == 128), "tile config");
-};
-
-template <int DPAD, int BN>
-__global__ void __launch_bounds__(320, 1)
-attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
-                  const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
-  using Cfg = Attn2Cfg<DPAD, BN>;
-  constexpr int ST = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_p = smem_q + Cfg::Q_BYTES;
-  uint8_t* smem_kv = smem_p + Cfg::P_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ST * Cfg::KV_STAGE);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;            // [ST]
-  uint64_t* v_full = k_full + ST;         // [ST]
-  uint64_t* kv_empty = v_full + ST;       // [ST]
-  uint64_t* s_full = kv_empty + ST;       // [2] per query tile
-  uint64_t* s_empty = s_full + 2;         // [2]
-  uint64_t* p_full = s_empty + 2;         // [2]
-  uint64_t* pv_done = p_full + 2;         // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_empty[t], 4);
-      mbar_init(&p_full[t], 4);
-      mbar_init(&pv_done[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  const int own_tiles = (p.tokens + BN - 1) / BN;
-  const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
-  const int m_pairs = (p.tokens + 255) / 256;
-  const int units_per_frame = p.heads * m_pairs;
-  const int num_units = p.n_frames * units_per_frame;
-
-  auto decode = [&](int unit, int& frame, int& head, int& m_pair, int& T) {
-    const int fk = unit / units_per_frame;
-    const int rem = unit % units_per_frame;
-    frame = (fk + p.first_bank_frame) % p.n_frames;
-    head = rem / m_pairs;
-    m_pair = rem % m_pairs;
-    const bool has_bank = p.bank_tokens > 0 && frame >= p.first_bank_frame;
-    T = own_tiles + (has_bank ? bank_tiles : 0);
-  };
-
-  if (warp < 2) {
-    if (warp == 0 && lane == 0) {
-      // ------------------------------------------------------------------------ TMA producer
-      uint32_t g = 0, uc = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
-        int frame, head, m_pair, T;
-        decode(unit, frame, head, m_pair, T);
-        mbar_wait(q_empty, (uc & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_2d(&tmQ, q_full, smem_q + t * Cfg::QT_BYTES + s * (128 * 128), head * DPAD + s * 64,
-                        frame * p.tokens + m_pair * 256 + t * 128);
-        const int bank_idx = (frame - p.first_bank_frame) / p.frames_per_bank;
-        for (int j = 0; j < T; ++j, ++g) {
-          const int stage = g % ST;
-          const uint32_t ph = (g / ST) & 1;
-          mbar_wait(&kv_empty[stage], ph ^ 1);
-          const bool own = j < own_tiles;
-          const CUtensorMap* mk = own ? &tmK : &tmBK;
-          const CUtensorMap* mv = own ? &tmV : &tmBV;
-          const int row = own ? frame * p.tokens + j * BN : bank_idx * p.bank_tokens + (j - own_tiles) * BN;
-          uint8_t* kd = smem_kv + stage * Cfg::KV_STAGE;
-          uint8_t* vd = kd + Cfg::K_BYTES;
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::K_BYTES);
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_2d(mk, &k_full[stage], kd + s * (BN * 128), head * DPAD + s * 64, row);
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::K_BYTES);
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_2d(mv, &v_full[stage], vd + s * (BN * 128), head * DPAD + s * 64, row);
-        }
-      }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);
-      uint32_t g = 0, uc = 0;
-      auto issue_qk = [&](int t, uint32_t gi, bool release_q) {
-        const int stage = gi % ST;
-        mbar_wait(&s_empty[t], (gi & 1) ^ 1);
-        mbar_wait(&k_full[stage], (gi / ST) & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + Cfg::TMEM_S + t * 128;
-        const uint32_t qa = smem_u32(smem_q + t * Cfg::QT_BYTES);
-        const uint32_t ka = smem_u32(smem_kv + stage * Cfg::KV_STAGE);
-#pragma unroll
-        for (int kk = 0; kk < DPAD / 16; ++kk) {
-          const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
-          const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
-          umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
-        }
-        umma_commit(&s_full[t]);
-        if (release_q) umma_commit(q_empty);
-      };
-      auto issue_pv = [&](int t, uint32_t gi, int j) {
-        const int stage = gi % ST;
-        mbar_wait(&p_full[t], gi & 1);
-        mbar_wait(&v_full[stage], (gi / ST) & 1);
-        tc_fence_after();
-        const uint32_t pa = smem_u32(smem_p + t * Cfg::PT_BYTES);
-        const uint32_t va = smem_u32(smem_kv + stage * Cfg::KV_STAGE + Cfg::K_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t da = umma_desc_k_sw128(pa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
-          const uint64_t db = umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128);
-          umma_f16_ss(tmem_base + Cfg::TMEM_O + t * DPAD, da, db, idesc_pv, (j | kk) != 0);
-        }
-        umma_commit(&pv_done[t]);
-        if (t == 1) umma_commit(&kv_empty[stage]);
-      };
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
-        int frame, head, m_pair, T;
-        decode(unit, frame, head, m_pair, T);
-        mbar_wait(q_full, uc & 1);
-        issue_qk(0, g, false);
-        issue_qk(1, g, T == 1);
-        for (int j = 0; j < T; ++j, ++g) {
-          issue_pv(0, g, j);
-          if (j + 1 < T) issue_qk(0, g + 1, false);
-          issue_pv(1, g, j);
-          if (j + 1 < T) issue_qk(1, g + 1, j + 2 == T);
-        }
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------------------- softmax + epilogue, tile t
-    const int t = (warp - 2) >> 2;
-    const int lane_group = warp & 3;
-    const int row = lane_group * 32 + lane;
-    const uint32_t t_lane = static_cast<uint32_t>(lane_group * 32) << 16;
-    const uint32_t t_s = tmem_base + Cfg::TMEM_S + t * 128 + t_lane;
-    const uint32_t t_o = tmem_base + Cfg::TMEM_O + t * DPAD + t_lane;
-    uint8_t* my_p = smem_p + t * Cfg::PT_BYTES;
-    uint32_t g = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      int frame, head, m_pair, T;
-      decode(unit, frame, head, m_pair, T);
-      float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < T; ++j, ++g) {
-        mbar_wait(&s_full[t], g & 1);
-        tc_fence_after();
-        uint32_t sr[BN];
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[t]);
-
-        const bool own = j < own_tiles;
-        const int jj = own ? j : j - own_tiles;
-        const int ntok = own ? p.tokens : p.bank_tokens;
-        const int valid = min(BN, ntok - jj * BN);
-        if (valid != BN) {
-#pragma unroll
-          for (int i = 0; i < BN; ++i)
-            if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
-        }
-        float mx8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
-#pragma unroll
-        for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sr[i]));
-        float tmax = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                           fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        tmax *= p.scale_log2;
-        float alpha = 1.f;
-        bool need = false;
-        if (j == 0) {
-          m_run = tmax;
-        } else if (tmax > m_run + kRescaleThreshold) {
-          alpha = fast_exp2(m_run - tmax);
-          m_run = tmax;
-          need = true;
-        }
-        const bool warp_need = __any_sync(0xffffffffu, need);
-        l_run *= alpha;
-
-        uint32_t pk[BN / 2];
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < BN; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
-          ls[(i >> 1) & 3] += p0 + p1;
-          const __half2 h = __floats2half2_rn(p0, p1);
-          pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-
-        if (g > 0) mbar_wait(&pv_done[t], (g - 1) & 1);
-        if (warp_need) {
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < DPAD / 32; ++c) {
-            uint32_t orr[32];
-            tmem_ld_32x32b_x32(t_o + c * 32, orr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + c * 32, orr);
-          }
-          tmem_st_wait();
-        }
-#pragma unroll
-        for (int c = 0; c < BN / 8; ++c) {
-          const int atom = c >> 3, cc = c & 7;
-          uint4 val = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          *reinterpret_cast<uint4*>(my_p + atom * (128 * 128) + row * 128 + ((cc ^ (row & 7)) << 4)) = val;
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
-      }
-      // ------------------------------------------------------------------ epilogue
-      mbar_wait(&pv_done[t], (g - 1) & 1);
-      tc_fence_after();
-      const float inv_l = 1.f / l_run;
-      const int q_idx = m_pair * 256 + t * 128 + row;
-      const bool row_ok = q_idx < p.tokens;
-      __half* dst = p.out + ((long long)frame * p.tokens + q_idx) * p.ldo + head * p.head_dim;
-#pragma unroll 1
-      for (int c = 0; c < DPAD / 32; ++c) {
-        if (c * 32 >= p.head_dim) break;
-        uint32_t orr[32];
-        tmem_ld_32x32b_x32(t_o + c * 32, orr);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (c * 32 + q * 8 < p.head_dim) {
-              __half2 o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = __floats2half2_rn(__uint_as_float(orr[q * 8 + 2 * i]) * inv_l,
-                                         __uint_as_float(orr[q * 8 + 2 * i + 1]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = *reinterpret_cast<uint4*>(o);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-
-// ============================================================================================================
-// v3: as v2 (two query tiles per CTA, ping-pong) but P never touches shared memory: the softmax warps write the fp16
-// probabilities back into tensor memory over the first BN/2 columns of their own S tile (tcgen05.st) and the P.V product
+// v3: two 128-query tiles per CTA, ping-pong (10 warps: TMA, MMA, 4 softmax warps per tile; one S buffer per tile at
+// TMEM columns [0,128) / [128,256), O_A / O_B behind them, K/V ring shared by both tiles), and P never touches shared
+// memory: the softmax warps write the fp16 probabilities back into tensor memory over the first BN/2 columns of their own S tile (tcgen05.st) and the P.V product
 // reads its A operand from TMEM (tcgen05.mma "TS" form). Per 128x128 tile this removes 32 KB of st.shared plus 32 KB of
 // tensor-core smem reads (of ~144 KB total), which was the co-limiter next to the MUFU exp throughput, and frees 64 KB
 // of shared memory for a deeper K/V ring (BN = 128 also for DPAD = 128).
@@ -725,7 +395,7 @@ struct Attn3Cfg {
   static_assert(DPAD % 64 == 0 && DPAD <= 128 && (BN == 64 || BN == 128), "tile config");
 };
 
-template <int DPAD, int BN, int EMU_NUM, int EMU_DEN>
+template <int DPAD, int BN>
 __global__ void __launch_bounds__(320, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
@@ -953,12 +623,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < BN; i += 2) {
-          // every EMU_PERIOD-th pair goes to the FMA-pipe polynomial, the rest to MUFU.EX2
-          const bool emu = (EMU_NUM > 0) && (((i >> 1) % EMU_DEN) < EMU_NUM);
-          const float a0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run);
-          const float a1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run);
-          const float p0 = emu ? poly_exp2(a0) : fast_exp2(a0);
-          const float p1 = emu ? poly_exp2(a1) : fast_exp2(a1);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
           ls[(i >> 1) & 3] += p0 + p1;
           const __half2 h = __floats2half2_rn(p0, p1);
           pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
@@ -1012,358 +678,22 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int DPAD, int BN, int EMU_NUM, int EMU_DEN>
+template <int DPAD, int BN>
 static int launch_attention3(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = Attn3Cfg<DPAD, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(attention3_kernel<DPAD, BN, EMU_NUM, EMU_DEN>,
+    AP_CHECK_CUDA(cudaFuncSetAttribute(attention3_kernel<DPAD, BN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int units = p.n_frames * p.heads * ((p.tokens + 255) / 256);
   const int grid = units < num_sms() ? units : num_sms();
-  attention3_kernel<DPAD, BN, EMU_NUM, EMU_DEN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
+  attention3_kernel<DPAD, BN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
                                                                                          maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
-
-// ============================================================================================================
-// v4: v3 (two query tiles per CTA, P kept in TMEM) with the S accumulator of EACH tile double-buffered (key tiles of
-// 64): Q.K^T of key tile j+1/j+2 is issued before the softmax of tile j has finished, so the softmax warps no longer sit
-// in the softmax -> P.V -> Q.K^T -> softmax dependency chain (ncu: 31 % of all warp samples of v3 were the wait for S).
-// TMEM: S slot (tile t, buffer b) at columns t*128 + b*64, O_t at 256 + t*DPAD (<= 512 for DPAD <= 128).
-// v3 notes: as v2 but P never touches shared memory: the softmax warps write the fp16
-// probabilities back into tensor memory over the first BN/2 columns of their own S tile (tcgen05.st) and the P.V product
-// reads its A operand from TMEM (tcgen05.mma "TS" form). Per 128x128 tile this removes 32 KB of st.shared plus 32 KB of
-// tensor-core smem reads (of ~144 KB total), which was the co-limiter next to the MUFU exp throughput, and frees 64 KB
-// of shared memory for a deeper K/V ring (BN = 128 also for DPAD = 128).
-// Ordering relies on (a) tcgen05.mma executing in issue order, (b) tcgen05.commit tracking ALL earlier MMAs of the
-// issuing thread: when s_full[t] of tile j fires, P.V of tile j-1 has completed, so S/P columns and O are quiescent.
-// ============================================================================================================
-template <int DPAD, int BN>
-struct Attn4Cfg {
-  static constexpr int SLABS = DPAD / 64;
-  static constexpr int QT_BYTES = 128 * DPAD * 2;
-  static constexpr int Q_BYTES = 2 * QT_BYTES;
-  static constexpr int K_BYTES = BN * DPAD * 2;
-  static constexpr int KV_STAGE = 2 * K_BYTES;
-  static constexpr int BUDGET = 227 * 1024 - 2048 - Q_BYTES;
-  static constexpr int STAGES_RAW = BUDGET / KV_STAGE;
-  static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * KV_STAGE + 1024 + 256;
-  static constexpr uint32_t TMEM_S = 0 /* + t*128 */, TMEM_O = 256 /* + t*DPAD */;
-  static_assert(STAGES >= 2, "need at least a double-buffered K/V ring");
-  static_assert(DPAD % 64 == 0 && DPAD <= 128 && BN == 64, "v4 uses 64-key tiles (double-buffered S)");
-};
-
-template <int DPAD, int BN, int EMU_NUM, int EMU_DEN>
-__global__ void __launch_bounds__(320, 1)
-attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
-                  const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
-  using Cfg = Attn4Cfg<DPAD, BN>;
-  constexpr int ST = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_kv = smem_q + Cfg::Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ST * Cfg::KV_STAGE);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;            // [ST]
-  uint64_t* v_full = k_full + ST;         // [ST]
-  uint64_t* kv_empty = v_full + ST;       // [ST]
-  uint64_t* s_full = kv_empty + ST;       // [4] per (query tile, S buffer)
-  uint64_t* p_full = s_full + 4;          // [4] per (query tile, S buffer): a softmax warpgroup may run up to two
-                                          // key tiles ahead of the MMA warp, so one barrier per buffer keeps every
-                                          // barrier at most one phase ahead of its waiter (parity waits alias otherwise)
-  uint64_t* o_done = p_full + 4;          // [2]
-  uint64_t* pv_done = o_done + 2;         // [2] (only waited on by the rare O-rescale path)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[2 * t], 1);
-      mbar_init(&s_full[2 * t + 1], 1);
-      mbar_init(&p_full[2 * t], 4);
-      mbar_init(&p_full[2 * t + 1], 4);
-      mbar_init(&o_done[t], 1);
-      mbar_init(&pv_done[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  const int own_tiles = (p.tokens + BN - 1) / BN;
-  const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
-  const int m_pairs = (p.tokens + 255) / 256;
-  const int units_per_frame = p.heads * m_pairs;
-  const int num_units = p.n_frames * units_per_frame;
-
-  auto decode = [&](int unit, int& frame, int& head, int& m_pair, int& T) {
-    const int fk = unit / units_per_frame;
-    const int rem = unit % units_per_frame;
-    frame = (fk + p.first_bank_frame) % p.n_frames;
-    head = rem / m_pairs;
-    m_pair = rem % m_pairs;
-    const bool has_bank = p.bank_tokens > 0 && frame >= p.first_bank_frame;
-    T = own_tiles + (has_bank ? bank_tiles : 0);
-  };
-
-  if (warp < 2) {
-    if (warp == 0 && lane == 0) {
-      // ------------------------------------------------------------------------ TMA producer
-      uint32_t g = 0, uc = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
-        int frame, head, m_pair, T;
-        decode(unit, frame, head, m_pair, T);
-        mbar_wait(q_empty, (uc & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_2d(&tmQ, q_full, smem_q + t * Cfg::QT_BYTES + s * (128 * 128), head * DPAD + s * 64,
-                        frame * p.tokens + m_pair * 256 + t * 128);
-        const int bank_idx = (frame - p.first_bank_frame) / p.frames_per_bank;
-        for (int j = 0; j < T; ++j, ++g) {
-          const int stage = g % ST;
-          const uint32_t ph = (g / ST) & 1;
-          mbar_wait(&kv_empty[stage], ph ^ 1);
-          const bool own = j < own_tiles;
-          const CUtensorMap* mk = own ? &tmK : &tmBK;
-          const CUtensorMap* mv = own ? &tmV : &tmBV;
-          const int row = own ? frame * p.tokens + j * BN : bank_idx * p.bank_tokens + (j - own_tiles) * BN;
-          uint8_t* kd = smem_kv + stage * Cfg::KV_STAGE;
-          uint8_t* vd = kd + Cfg::K_BYTES;
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::K_BYTES);
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_2d(mk, &k_full[stage], kd + s * (BN * 128), head * DPAD + s * 64, row);
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::K_BYTES);
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_2d(mv, &v_full[stage], vd + s * (BN * 128), head * DPAD + s * 64, row);
-        }
-      }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, DPAD, 0, 1);
-      uint32_t g = 0, uc = 0;
-      auto issue_qk = [&](int t, uint32_t gi, bool release_q) {
-        const int stage = gi % ST;
-        mbar_wait(&k_full[stage], (gi / ST) & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + Cfg::TMEM_S + t * 128 + (gi & 1) * 64;
-        const uint32_t qa = smem_u32(smem_q + t * Cfg::QT_BYTES);
-        const uint32_t ka = smem_u32(smem_kv + stage * Cfg::KV_STAGE);
-#pragma unroll
-        for (int kk = 0; kk < DPAD / 16; ++kk) {
-          const uint64_t da = umma_desc_k_sw128(qa + (kk / 4) * (128 * 128) + (kk % 4) * 32);
-          const uint64_t db = umma_desc_k_sw128(ka + (kk / 4) * (BN * 128) + (kk % 4) * 32);
-          umma_f16_ss(d_tmem, da, db, idesc_qk, kk != 0);
-        }
-        umma_commit(&s_full[2 * t + (gi & 1)]);
-        if (release_q) umma_commit(q_empty);
-      };
-      auto issue_pv = [&](int t, uint32_t gi, int j, bool last) {
-        const int stage = gi % ST;
-        mbar_wait(&p_full[2 * t + (gi & 1)], (gi >> 1) & 1);
-        mbar_wait(&v_full[stage], (gi / ST) & 1);
-        tc_fence_after();
-        const uint32_t a_tmem = tmem_base + Cfg::TMEM_S + t * 128 + (gi & 1) * 64;   // P aliases its S buffer
-        const uint32_t va = smem_u32(smem_kv + stage * Cfg::KV_STAGE + Cfg::K_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t db = umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128);
-          umma_f16_ts(tmem_base + Cfg::TMEM_O + t * DPAD, a_tmem + kk * 8, db, idesc_pv, (j | kk) != 0);
-        }
-        umma_commit(&pv_done[t]);
-        if (t == 1) umma_commit(&kv_empty[stage]);
-        if (last) umma_commit(&o_done[t]);
-      };
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
-        int frame, head, m_pair, T;
-        decode(unit, frame, head, m_pair, T);
-        mbar_wait(q_full, uc & 1);
-        issue_qk(0, g, false);
-        issue_qk(1, g, T == 1);
-        if (T > 1) {
-          issue_qk(0, g + 1, false);
-          issue_qk(1, g + 1, T == 2);
-        }
-        for (int j = 0; j < T; ++j, ++g) {
-          issue_pv(0, g, j, j + 1 == T);
-          if (j + 2 < T) issue_qk(0, g + 2, false);
-          issue_pv(1, g, j, j + 1 == T);
-          if (j + 2 < T) issue_qk(1, g + 2, j + 3 == T);
-        }
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------------------- softmax + epilogue, tile t
-    const int t = (warp - 2) >> 2;
-    const int lane_group = warp & 3;
-    const int row = lane_group * 32 + lane;
-    const uint32_t t_lane = static_cast<uint32_t>(lane_group * 32) << 16;
-    const uint32_t t_s0 = tmem_base + Cfg::TMEM_S + t * 128 + t_lane;
-    const uint32_t t_o = tmem_base + Cfg::TMEM_O + t * DPAD + t_lane;
-    uint32_t g = 0, uc = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
-      int frame, head, m_pair, T;
-      decode(unit, frame, head, m_pair, T);
-      float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < T; ++j, ++g) {
-        const uint32_t t_s = t_s0 + (g & 1) * 64;
-        mbar_wait(&s_full[2 * t + (g & 1)], (g >> 1) & 1);
-        tc_fence_after();
-        uint32_t sr[BN];
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
-        tmem_ld_wait();
-
-        const bool own = j < own_tiles;
-        const int jj = own ? j : j - own_tiles;
-        const int ntok = own ? p.tokens : p.bank_tokens;
-        const int valid = min(BN, ntok - jj * BN);
-        if (valid != BN) {
-#pragma unroll
-          for (int i = 0; i < BN; ++i)
-            if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
-        }
-        float mx8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
-#pragma unroll
-        for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sr[i]));
-        float tmax = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                           fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        tmax *= p.scale_log2;
-        float alpha = 1.f;
-        bool need = false;
-        if (j == 0) {
-          m_run = tmax;
-        } else if (tmax > m_run + kRescaleThreshold) {
-          alpha = fast_exp2(m_run - tmax);
-          m_run = tmax;
-          need = true;
-        }
-        const bool warp_need = __any_sync(0xffffffffu, need);
-        l_run *= alpha;
-        if (warp_need) {   // rare: wait until P.V of the previous tile has completed, then O is quiescent
-          mbar_wait(&pv_done[t], (g - 1) & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < DPAD / 32; ++c) {
-            uint32_t orr[32];
-            tmem_ld_32x32b_x32(t_o + c * 32, orr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + c * 32, orr);
-          }
-        }
-
-        uint32_t pk[BN / 2];
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < BN; i += 2) {
-          // every EMU_PERIOD-th pair goes to the FMA-pipe polynomial, the rest to MUFU.EX2
-          const bool emu = (EMU_NUM > 0) && (((i >> 1) % EMU_DEN) < EMU_NUM);
-          const float a0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run);
-          const float a1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run);
-          const float p0 = emu ? poly_exp2(a0) : fast_exp2(a0);
-          const float p1 = emu ? poly_exp2(a1) : fast_exp2(a1);
-          ls[(i >> 1) & 3] += p0 + p1;
-          const __half2 h = __floats2half2_rn(p0, p1);
-          pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-        // P (fp16 pairs) -> TMEM, over the first BN/2 columns of this tile's S
-#pragma unroll
-        for (int c = 0; c < BN / 64; ++c) tmem_st_32x32b_x32(t_s + c * 32, pk + c * 32);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * t + (g & 1)]);
-      }
-      // ------------------------------------------------------------------ epilogue
-      mbar_wait(&o_done[t], uc & 1);
-      tc_fence_after();
-      const float inv_l = 1.f / l_run;
-      const int q_idx = m_pair * 256 + t * 128 + row;
-      const bool row_ok = q_idx < p.tokens;
-      __half* dst = p.out + ((long long)frame * p.tokens + q_idx) * p.ldo + head * p.head_dim;
-#pragma unroll 1
-      for (int c = 0; c < DPAD / 32; ++c) {
-        if (c * 32 >= p.head_dim) break;
-        uint32_t orr[32];
-        tmem_ld_32x32b_x32(t_o + c * 32, orr);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (c * 32 + q * 8 < p.head_dim) {
-              __half2 o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = __floats2half2_rn(__uint_as_float(orr[q * 8 + 2 * i]) * inv_l,
-                                         __uint_as_float(orr[q * 8 + 2 * i + 1]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = *reinterpret_cast<uint4*>(o);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-template <int DPAD, int BN, int EMU_NUM, int EMU_DEN>
-static int launch_attention4(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
-  using Cfg = Attn4Cfg<DPAD, BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(attention4_kernel<DPAD, BN, EMU_NUM, EMU_DEN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  const int units = p.n_frames * p.heads * ((p.tokens + 255) / 256);
-  const int grid = units < num_sms() ? units : num_sms();
-  attention4_kernel<DPAD, BN, EMU_NUM, EMU_DEN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
-                                                                                         maps[3], maps[4], p);
-  AP_CHECK_CUDA(cudaGetLastError());
-  return AP_OK;
-}
-
 
 // ============================================================================================================
 // v5: ONE 128-query tile per CTA, TWO CTAs per SM. S is double-buffered in TMEM (Q.K^T of key tile j+1 is issued before
@@ -1384,7 +714,6 @@ struct Attn5Cfg {
   static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs must fit one SM");
 };
 
-template <int EMU_NUM, bool DENOM, bool PREFETCH>
 __global__ void __launch_bounds__(192, 2)
 attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
@@ -1541,23 +870,13 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       int frame, head, m_tile, T;
       decode(unit, frame, head, m_tile, T);
       float m_run = -INFINITY, l_run = 0.f;
-      if (PREFETCH) {   // S of the unit's first key tile; later tiles are fetched while the previous P store drains
-        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_s0 = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s0 + c * 32, sr + c * 32);
-        tmem_ld_wait();
-      }
       for (int j = 0; j < T; ++j, ++g) {
         const uint32_t t_s = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
-        if (!PREFETCH) {
-          mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-          tc_fence_after();
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
-          tmem_ld_wait();
-        }
+        for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+        tmem_ld_wait();
         const bool own = j < own_tiles;
         const int jj = own ? j : j - own_tiles;
         const int ntok = own ? p.tokens : p.bank_tokens;
@@ -1585,7 +904,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           need = true;
         }
         const bool warp_need = __any_sync(0xffffffffu, need);
-        if (!DENOM) l_run *= alpha;
+        l_run *= alpha;
         if (warp_need) {   // rare: O may only be touched once P.V of the previous key tile has completed
           mbar_wait(pv_done, (g - 1) & 1);
           tc_fence_after();
@@ -1603,42 +922,24 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < BN; i += 2) {
-          const bool emu = (EMU_NUM > 0) && (((i >> 1) & 3) < EMU_NUM);
-          const float a0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run);
-          const float a1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run);
-          const float p0 = emu ? poly_exp2(a0) : fast_exp2(a0);
-          const float p1 = emu ? poly_exp2(a1) : fast_exp2(a1);
-          if (!DENOM) ls[(i >> 1) & 3] += p0 + p1;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
+          ls[(i >> 1) & 3] += p0 + p1;
           const __half2 h = __floats2half2_rn(p0, p1);
           pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        if (!DENOM) l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         // P (48 packed columns) -> TMEM over the first half of this S buffer
         tmem_st_32x32b_x32(t_s, pk);
         tmem_st_32x32b_x16(t_s + 32, pk + 32);
-        if (PREFETCH && j + 1 < T) {   // fetch S of the next key tile while the P store drains
-          const uint32_t gn = g + 1;
-          mbar_wait(&s_full[gn & 1], (gn >> 1) & 1);
-          tc_fence_after();
-          const uint32_t t_sn = tmem_base + ((gn & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(t_sn + c * 32, sr + c * 32);
-        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g & 1]);
-        if (PREFETCH && j + 1 < T) tmem_ld_wait();
       }
       // ------------------------------------------------------------------ epilogue
       mbar_wait(o_done, uc & 1);
       tc_fence_after();
-      if (DENOM) {   // V carries 1.0 in padded column head_dim: that accumulator column is sum_j P_ij
-        uint32_t lv[1];
-        tmem_ld_32x32b_x1(t_o + p.head_dim, lv);
-        tmem_ld_wait();
-        l_run = __uint_as_float(lv[0]);
-      }
       const float inv_l = 1.f / l_run;
       const int q_idx = m_tile * 128 + row;
       const bool row_ok = q_idx < p.tokens;
@@ -1676,34 +977,16 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int EMU_NUM, bool DENOM, bool PREFETCH>
 static int launch_attention5(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = Attn5Cfg;
   static bool attr_set = false;
-  auto kern = attention5_kernel<EMU_NUM, DENOM, PREFETCH>;
   if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(attention5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int max_ctas = 2 * num_sms();
   const int grid = p.num_units < max_ctas ? p.num_units : max_ctas;
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
-  AP_CHECK_CUDA(cudaGetLastError());
-  return AP_OK;
-}
-
-template <int DPAD, int BN>
-static int launch_attention2(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
-  using Cfg = Attn2Cfg<DPAD, BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(attention2_kernel<DPAD, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  const int units = p.n_frames * p.heads * ((p.tokens + 255) / 256);
-  const int grid = units < num_sms() ? units : num_sms();
-  attention2_kernel<DPAD, BN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  attention5_kernel<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -1730,8 +1013,7 @@ using namespace ap;
 extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, long long ld_qkv, const void* bank_k,
                                 const void* bank_v, long long ld_bank, int bank_tokens, int n_banks, int n_frames,
                                 int tokens, int heads, int head_dim, int dpad, int first_bank_frame,
-                                int frames_per_bank, float scale, void* out, long long ldo, int flags,
-                                void* stream) {
+                                int frames_per_bank, float scale, void* out, long long ldo, void* stream) {
   AP_REQUIRE(q && k && v && out, "attention: null pointer");
   AP_REQUIRE(dpad == 64 || dpad == 128 || dpad == 192, "attention: dpad must be 64/128/192 (got %d)", dpad);
   AP_REQUIRE(head_dim % 8 == 0 && head_dim <= dpad, "attention: head_dim %d must be a multiple of 8 and <= dpad", head_dim);
@@ -1743,17 +1025,16 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
   // v3 (two query tiles per CTA, P kept in TMEM) for dpad <= 128; v1 for dpad = 192 / tiny token counts.
   // AP_ATTENTION_V1=1 / AP_ATTENTION_V2=1 select the older variants (A/B timing).
   static const bool force_v1 = (getenv("AP_ATTENTION_V1") != nullptr);
-  static const bool force_v2 = (getenv("AP_ATTENTION_V2") != nullptr);
-  // v4 (double-buffered S, 64-key tiles) measured slower than v3 (3.56 vs 2.67 ms on the 64x64 level: the per-tile fixed
-  // costs double) and is kept selectable (AP_ATTENTION_V4=1) for further tuning only.
-  static const bool force_v4 = (getenv("AP_ATTENTION_V4") != nullptr);
+  // kernel generations (measurements: profiles/r01_ncu_full_top_kernels.md):
+  //   v5  d <= 64 and more than one query tile: one query tile per CTA, two CTAs per SM, S double-buffered, P in TMEM
+  //   v3  d <= 128: two query tiles per CTA, P in TMEM
+  //   v1  d <= 192 or at most 128 tokens: one query tile per CTA, S double-buffered, P through shared memory
+  // AP_ATTENTION_V5=0 / AP_ATTENTION_V1=1 fall back to the older generation for A/B timing.
   static const int v5_env = getenv("AP_ATTENTION_V5") ? atoi(getenv("AP_ATTENTION_V5")) : -1;
   const bool two_tiles = !force_v1 && dpad <= 128 && tokens > 128;
-  const bool use_v5 = (v5_env != 0) && !force_v1 && !force_v2 && !force_v4 && dpad == 64 && tokens > 128;
-  const bool use_v4 = two_tiles && force_v4 && !use_v5;
-  const bool use_v3 = two_tiles && !force_v2 && !force_v4 && !use_v5;
-  const bool use_v2 = two_tiles && force_v2;
-  const int bn = use_v5 ? 96 : use_v4 ? 64 : (use_v3 ? 128 : (use_v2 ? (dpad == 64 ? 128 : 64) : (dpad == 192 ? 64 : 128)));
+  const bool use_v5 = two_tiles && v5_env != 0 && dpad == 64;
+  const bool use_v3 = two_tiles && !use_v5;
+  const int bn = use_v5 ? 96 : (use_v3 ? 128 : (dpad == 192 ? 64 : 128));
 
   AttnParams p{};
   p.n_frames = n_frames;
@@ -1795,46 +1076,8 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
     maps[4] = maps[2];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_v5) {
-    // A/B switches kept for profiling: AP_ATTENTION_EMU=1 evaluates 1/4 of the exponentials on the FMA pipe,
-    // AP_ATTENTION_PREFETCH=1 fetches S(j+1) under the P(j) store, AP_ATTENTION_DENOM=1 honours AP_ATTN_DENOM_IN_V
-    // (all three measured slower on B200 - 2.47 / 2.46 / 2.42 ms against 2.25 ms at the 64x64 level - see
-    // profiles/r01_ncu_full_top_kernels.md; the default therefore sums the probabilities on the CUDA cores).
-    static const int emu5 = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : 0;
-    static const bool prefetch = getenv("AP_ATTENTION_PREFETCH") != nullptr;
-    static const bool use_denom = getenv("AP_ATTENTION_DENOM") != nullptr;
-    const bool denom = (flags & AP_ATTN_DENOM_IN_V) != 0 && head_dim < dpad && use_denom;
-    if (prefetch) return denom ? launch_attention5<0, true, true>(maps, p, st) : launch_attention5<0, false, true>(maps, p, st);
-    if (emu5 == 1) return denom ? launch_attention5<1, true, false>(maps, p, st) : launch_attention5<1, false, false>(maps, p, st);
-    return denom ? launch_attention5<0, true, false>(maps, p, st) : launch_attention5<0, false, false>(maps, p, st);
-  }
-  if (use_v4) {
-    static const int emu_env4 = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : -1;
-    const int emu = emu_env4 >= 0 ? emu_env4 : 0;
-    if (dpad == 64) {
-      if (emu == 0) return launch_attention4<64, 64, 0, 4>(maps, p, st);
-      if (emu == 1) return launch_attention4<64, 64, 1, 4>(maps, p, st);
-      return launch_attention4<64, 64, 2, 4>(maps, p, st);
-    }
-    if (emu == 0) return launch_attention4<128, 64, 0, 4>(maps, p, st);
-    if (emu == 1) return launch_attention4<128, 64, 1, 4>(maps, p, st);
-    return launch_attention4<128, 64, 2, 4>(maps, p, st);
-  }
-  if (use_v3) {
-    // fraction of exponentials evaluated on the FMA pipe: d=40 tiles are exp-bound (half), d=80 less so (quarter).
-    // AP_ATTENTION_EMU=0|1|2 overrides (0 = none, 1 = 1/4, 2 = 1/2) for A/B timing.
-    static const int emu_env = getenv("AP_ATTENTION_EMU") ? atoi(getenv("AP_ATTENTION_EMU")) : -1;
-    const int emu = emu_env >= 0 ? emu_env : 0;
-    if (dpad == 64) {
-      if (emu == 0) return launch_attention3<64, 128, 0, 4>(maps, p, st);
-      if (emu == 1) return launch_attention3<64, 128, 1, 4>(maps, p, st);
-      return launch_attention3<64, 128, 2, 4>(maps, p, st);
-    }
-    if (emu == 0) return launch_attention3<128, 128, 0, 4>(maps, p, st);
-    if (emu == 1) return launch_attention3<128, 128, 1, 4>(maps, p, st);
-    return launch_attention3<128, 128, 2, 4>(maps, p, st);
-  }
-  if (use_v2) return dpad == 64 ? launch_attention2<64, 128>(maps, p, st) : launch_attention2<128, 64>(maps, p, st);
+  if (use_v5) return launch_attention5(maps, p, st);
+  if (use_v3) return dpad == 64 ? launch_attention3<64, 128>(maps, p, st) : launch_attention3<128, 128>(maps, p, st);
   if (dpad == 64) return launch_attention<64, 128>(maps, p, st);
   if (dpad == 128) return launch_attention<128, 128>(maps, p, st);
   return launch_attention<192, 64>(maps, p, st);

@@ -215,24 +215,12 @@ def pad_head_rows(w: torch.Tensor, heads: int, dpad: int) -> torch.Tensor:
     return out.reshape(heads * dpad, k).contiguous()
 
 
-def ones_column_bias(heads: int, head_dim: int, dpad: int, sections: int, v_section: int,
-                     device) -> torch.Tensor | None:
-    """fp32 GEMM bias for a fused [.. | v] projection with padded heads: 1.0 at the first padded column of every head of
-    the V section (weights there are zero rows, so V[:, h*dpad + head_dim] == 1), else 0. None if there is no padding."""
-    if head_dim >= dpad:
-        return None
-    b = torch.zeros(sections, heads, dpad, dtype=torch.float32, device=device)
-    b[v_section, :, head_dim] = 1.0
-    return b.reshape(-1).contiguous()
-
-
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_frames: int, tokens: int, heads: int,
               head_dim: int, dpad: int, bank_k: torch.Tensor | None = None, bank_v: torch.Tensor | None = None,
               bank_tokens: int = 0, n_banks: int = 0, first_bank_frame: int = 0, frames_per_bank: int = 1,
-              scale: float | None = None, out: torch.Tensor | None = None, denom_in_v: bool = False) -> torch.Tensor:
+              scale: float | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """q/k/v: column-slices [n_frames*tokens, heads*dpad] of one fp16 buffer (same row stride); returns
-    [n_frames*tokens, heads*head_dim]. denom_in_v: v / bank_v carry 1.0 in padded column head_dim of every head
-    (see ones_column_bias), letting the kernel take the softmax denominator from the P.V accumulator."""
+    [n_frames*tokens, heads*head_dim]."""
     _ensure(q)
     rows = n_frames * tokens
     for t in (q, k, v):
@@ -250,7 +238,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_frames: int, 
     rc = lib().ap_attention_f16(ptr(q), ptr(k), ptr(v), LL(q.stride(0)), ptr(bank_k), ptr(bank_v), LL(ld_bank),
                                 I(bank_tokens), I(n_banks), I(n_frames), I(tokens), I(heads), I(head_dim), I(dpad),
                                 I(first_bank_frame), I(frames_per_bank), _lib.c_float(scale), ptr(out),
-                                LL(out.stride(0)), I(1 if (denom_in_v and head_dim < dpad) else 0), stream_ptr())
+                                LL(out.stride(0)), stream_ptr())
     check(rc, "ap_attention_f16")
     _count()
     return out

@@ -94,16 +94,11 @@ int ap_softmax_rows_f16(const void* x, void* out, long long rows, int cols, long
  * out: [n_frames*tokens, ldo], head h at columns [h*head_dim, (h+1)*head_dim).
  * Replaces F.scaled_dot_product_attention under ReferenceAttentionControl's read-mode forward, including the CFG
  * redo for the unconditional half (reference src/models/mutual_self_attention.py:147-186; src/models/attention.py:323-330).
- * flags: AP_ATTN_DENOM_IN_V = the caller guarantees that v and bank_v hold 1.0 in the padded column h*dpad + head_dim
- * of every head (needs head_dim < dpad); the kernel may then read the softmax denominator from that accumulator column
- * instead of summing the probabilities on the CUDA cores (a hint: measured slower on B200, so the kernels only honour it
- * when AP_ATTENTION_DENOM is set in the environment). Results are identical with or without the flag.
  */
-#define AP_ATTN_DENOM_IN_V 1
 int ap_attention_f16(const void* q, const void* k, const void* v, long long ld_qkv, const void* bank_k,
                      const void* bank_v, long long ld_bank, int bank_tokens, int n_banks, int n_frames, int tokens,
                      int heads, int head_dim, int dpad, int first_bank_frame, int frames_per_bank, float scale,
-                     void* out, long long ldo, int flags, void* stream);
+                     void* out, long long ldo, void* stream);
 
 /*
  * Temporal attention core of the motion module: softmax over the F frames of each (batch, position, head).

@@ -86,8 +86,7 @@ def _attn_ref(q, k, v, scale):
     (1024, 16, 88, 2, None), # PoseGuider head layout
     (100, 2, 40, 3, 1),      # ragged token count
 ])
-@pytest.mark.parametrize("denom_in_v", [False, True])
-def test_attention(cuda_dev, tokens, heads, d, frames, bank_from, denom_in_v):
+def test_attention(cuda_dev, tokens, heads, d, frames, bank_from):
     from aniportrait_b200 import ops
     dpad = ops.head_pad(d)
     rows = frames * tokens
@@ -95,21 +94,17 @@ def test_attention(cuda_dev, tokens, heads, d, frames, bank_from, denom_in_v):
     qkv_true = (torch.randn(rows, 3, heads, d, generator=g) * 1.5).to(torch.float16)
     qkv = torch.zeros(rows, 3, heads, dpad, dtype=torch.float16)
     qkv[..., :d] = qkv_true
-    if denom_in_v:   # the layout the model produces through ops.ones_column_bias
-        qkv[:, 2, :, d] = 1.0
     qkv = qkv.reshape(rows, 3 * heads * dpad).to(cuda_dev)
     hp = heads * dpad
     q, k, v = qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:]
-    kwargs = dict(denom_in_v=denom_in_v)
+    kwargs = {}
     bank_true = None
     if bank_from is not None:
         bank_true = (torch.randn(tokens, 2, heads, d, generator=g) * 1.5).to(torch.float16)
         bank = torch.zeros(tokens, 2, heads, dpad, dtype=torch.float16)
         bank[..., :d] = bank_true
-        if denom_in_v:
-            bank[:, 1, :, d] = 1.0
         bank = bank.reshape(tokens, 2 * hp).to(cuda_dev)
-        kwargs = dict(denom_in_v=denom_in_v, bank_k=bank[:, :hp], bank_v=bank[:, hp:], bank_tokens=tokens, n_banks=1,
+        kwargs = dict(bank_k=bank[:, :hp], bank_v=bank[:, hp:], bank_tokens=tokens, n_banks=1,
                       first_bank_frame=bank_from, frames_per_bank=frames)
     out = ops.attention(q, k, v, frames, tokens, heads, d, dpad, **kwargs)
     torch.cuda.synchronize()
@@ -139,11 +134,9 @@ def test_attention_large_logits(cuda_dev):
     qkv_true = qkv_true.to(torch.float16)
     qkv = torch.zeros(frames * tokens, 3, heads, dpad, dtype=torch.float16)
     qkv[..., :d] = qkv_true
-    qkv[:, 2, :, d] = 1.0
     hp = heads * dpad
     qkv = qkv.reshape(-1, 3 * hp).to(cuda_dev)
-    out = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], frames, tokens, heads, d, dpad,
-                        denom_in_v=True)
+    out = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], frames, tokens, heads, d, dpad)
     qt = qkv_true.to(cuda_dev).view(frames, tokens, 3, heads, d).permute(2, 0, 3, 1, 4)
     ref = _attn_ref(qt[0], qt[1], qt[2], d ** -0.5).permute(0, 2, 1, 3).reshape(frames * tokens, heads * d)
     assert rel_l2(out, ref) < 3e-3
