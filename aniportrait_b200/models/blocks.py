@@ -22,7 +22,11 @@ class RunCtx:
     """Per-forward state threaded through the blocks."""
 
     def __init__(self, batch: int, frames: int, temb_act: torch.Tensor | None, ehs: torch.Tensor | None,
-                 ehs_key=None):
+                 ehs_key=None, ref_branch=None):
+        # ref_branch: None = the reference's layout (both CFG branches in the batch when the reader was built with
+        # do_classifier_free_guidance); "uncond" / "cond" = this call carries ONE branch of a CFG reader (multi-GPU
+        # (window, branch) work units): uncond never reads the bank, cond reads the conditional bank for every frame
+        self.ref_branch = ref_branch
         self.B = batch              # CFG branches x videos
         self.F = frames             # frames per batch element (1 for the 2-D ReferenceNet)
         self.temb_act = temb_act    # SiLU(time embedding) [B, 1280] fp16
@@ -213,12 +217,15 @@ class BasicTransformerBlock(nn.Module):
         if ehs is None or ehs.shape[1] != 1:
             raise NotImplementedError("attn2 with more than one encoder token is not part of the AniPortrait hot path")
         key = (ctx.ehs_key, ehs.data_ptr(), ehs._version, id(pk))
-        if self._attn2_const is None or self._attn2_const[0] != key:
+        cache = self._attn2_const if isinstance(self._attn2_const, dict) else {}
+        if key not in cache:
             e = ehs.reshape(ehs.shape[0], -1).contiguous()
             v = ops.gemm(e, pk["wv2"])
-            c = ops.gemm(v, pk["wo2"], bias=(pk["bo2"] + pk["bo"]), out_f32=True)
-            self._attn2_const = (key, c)
-        return self._attn2_const[1], 1
+            if len(cache) >= 4:       # a video needs at most 3 (both branches together, uncond alone, cond alone)
+                cache.clear()
+            cache[key] = ops.gemm(v, pk["wo2"], bias=(pk["bo2"] + pk["bo"]), out_f32=True)
+            self._attn2_const = cache
+        return cache[key], 1
 
     def _bank_projection(self, pk, n_tokens):
         """K/V of the ReferenceNet bank under THIS block's to_k/to_v. The bank is step- and frame-invariant, so it is
@@ -249,10 +256,15 @@ class BasicTransformerBlock(nn.Module):
         qkv = ops.gemm(n1, pk["wqkv"])
         q, k, v = qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:]
         kw = {}
-        if self._ref_mode == "read" and len(self.bank) > 0:
+        if self._ref_mode == "read" and len(self.bank) > 0 and ctx.ref_branch != "uncond":
             kv, nb = self._bank_projection(pk, tokens)
             bank_tokens = self.bank[0].shape[1]
-            if self._ref_cfg:
+            if self._ref_cfg and ctx.ref_branch == "cond":
+                # single-branch call of a CFG reader: every frame reads the bank of the conditional ReferenceNet pass
+                nbh = nb // 2
+                kw = dict(bank_k=kv[nbh * bank_tokens:, :hp], bank_v=kv[nbh * bank_tokens:, hp:],
+                          bank_tokens=bank_tokens, n_banks=nb - nbh, first_bank_frame=0, frames_per_bank=ctx.F)
+            elif self._ref_cfg:
                 # frames of the first half of the batch are the unconditional branch: no reference keys
                 # (mutual_self_attention.py:166-186); frame f of the second half reads bank[f // F] (:148-157)
                 first = (ctx.B // 2) * ctx.F

@@ -206,7 +206,7 @@ class UNet3DConditionModel(ModelBase):
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward_nhwc(self, x: torch.Tensor, batch: int, frames: int, timestep, encoder_hidden_states,
-                     pose_nhwc=None) -> torch.Tensor:
+                     pose_nhwc=None, ref_branch=None) -> torch.Tensor:
         """x: [(batch frames), H, W, 64] fp16 (4 latent channels zero padded to 64). pose_nhwc: 5 maps, each
         [(batch frames) | frames, h, w, C] (a [frames,...] map is shared by all CFG branches).
         Returns [(batch frames), H, W, out_channels] fp16."""
@@ -223,7 +223,7 @@ class UNet3DConditionModel(ModelBase):
         t_emb = ops.timestep_embedding(t.contiguous(), self.conv_in.out_channels)
         emb = self.time_embedding.run(t_emb)
         ehs = encoder_hidden_states.to(torch.float16).contiguous() if encoder_hidden_states is not None else None
-        ctx = RunCtx(batch, frames, ops.silu(emb), ehs, ehs_key=None)
+        ctx = RunCtx(batch, frames, ops.silu(emb), ehs, ehs_key=None, ref_branch=ref_branch)   # see RunCtx
 
         def add_pose(x, k):
             if pose_nhwc is None:

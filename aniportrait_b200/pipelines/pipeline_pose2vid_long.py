@@ -26,7 +26,7 @@ import torch
 
 from .. import ops
 from ..models.mutual_self_attention import ReferenceAttentionControl
-from .sharding import plan_windows, windows_of_rank
+from .sharding import plan_units, plan_windows, windows_of_rank
 from .image_processor import VaeImageProcessor
 
 
@@ -208,6 +208,18 @@ class Pose2VideoPipeline:
         pred = self.denoising_unet.forward_nhwc(x, S.dup, idx.numel(), S.t_dev, S.ehs, S.win_pose[k])
         ops.scatter_accumulate(pred, idx, S.acc)
 
+    def _unit_step(self, S, k, branch):
+        """One (window, CFG-branch) work unit. "both" = the reference's layout (both branches in one batch); "uncond" /
+        "cond" = a batch-1 UNet call for one branch (sharded mode only), accumulated into that branch's plane."""
+        if branch == "both":
+            return self._window_step(S, k)
+        idx = S.win_idx[k]
+        b = 0 if branch == "uncond" else 1
+        x = ops.gather_window(S.lat, idx, 1, 64)
+        pred = self.denoising_unet.forward_nhwc(x, 1, idx.numel(), S.t_dev, S.ehs[b:b + 1], S.win_pose[k],
+                                                ref_branch=branch)
+        ops.scatter_accumulate(pred, idx, S.acc[b:b + 1])
+
     def _reset_block_caches(self):
         """Drop step-invariant tensors cached on the transformer blocks (bank K/V, attn2 constants) so that the next pass
         recomputes them — required right before a graph capture, otherwise the work would be missing from the graph."""
@@ -339,8 +351,16 @@ class Pose2VideoPipeline:
         L, h, w = latents.shape[2], latents.shape[3], latents.shape[4]
         windows, inv_count = plan_windows(L, num_inference_steps, context_schedule, context_frames, context_stride,
                                           context_overlap)
-        shard = world > 1 and dist_mode == "windows"
-        my_windows = windows_of_rank(windows, rank, world, shard)
+        shard = world > 1 and dist_mode in ("windows", "window_branches")
+        if shard and dist_mode == "window_branches":
+            # (window, CFG branch) units: twice as many, smaller units -> better balance when windows < 2 x ranks
+            mine = plan_units(len(windows), cfg, world)[rank]
+            ids = sorted({k for k, _ in mine})
+            my_windows = [windows[k] for k in ids]
+            units = [(ids.index(k), br) for k, br in mine]
+        else:
+            my_windows = windows_of_rank(windows, rank, world, shard)
+            units = [(k, "both") for k in range(len(my_windows))]
         inv_count = inv_count.to(device=device, dtype=torch.float32)
         clip_is_embed = clip_image_embeds is not None
         clip_in = clip_image_embeds if clip_is_embed else clip_pixels
@@ -394,8 +414,8 @@ class Pose2VideoPipeline:
                         g.replay()
                         ops._count(n)
                 else:
-                    for k in range(len(S.win_idx)):
-                        self._window_step(S, k)
+                    for k, branch in units:
+                        self._unit_step(S, k, branch)
                 if shard:
                     torch.distributed.all_reduce(acc)
                 a_t, a_p = self._alpha_pair(t)
@@ -456,9 +476,12 @@ class Pose2VideoPipeline:
              None       every rank computes the whole video redundantly (reference behaviour)
              "windows"  the windows of ONE long video are sharded over ranks; fp32 prediction accumulator all-reduced
                         (NCCL) once per step; every rank ends with the full latents and video
+             "window_branches"  as "windows" with (window, CFG branch) work units: a rank may run the unconditional or
+                        the conditional half of a window as a batch-1 UNet call (22 units instead of 11
+                        windows at L=128 -> 8 GPUs stay busy)
              "clips"    every rank denoises its OWN clip (its own pose_images / latents); fully independent ranks (the
                         1 ms ReferenceNet pass is recomputed per rank rather than broadcast), no collective
-           In "windows" mode rank 0 alone runs the ReferenceNet and broadcasts the 16 banks (NCCL)."""
+           In the sharded modes rank 0 alone runs the ReferenceNet and broadcasts the 16 banks (NCCL)."""
         if eta != 0.0:
             raise NotImplementedError("eta > 0 is unused by AniPortrait")
         if context_batch_size != 1:

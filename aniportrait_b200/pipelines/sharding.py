@@ -34,6 +34,34 @@ def windows_of_rank(windows: List[List[int]], rank: int, world: int, shard: bool
     return [wd for i, wd in enumerate(windows) if i % world == rank]
 
 
+def plan_units(n_windows: int, cfg: bool, world: int, cond_cost: float = 1.2) -> List[List[tuple]]:
+    """(window, CFG branch) work units of one denoising step, statically assigned to ranks (window-only
+    granularity caps an 8-GPU run of 11 windows at 5.5x). Longest-processing-time-first over the unit costs (the
+    conditional branch attends to twice the keys: ~1.2x), ties broken by index, so every rank derives the same plan.
+    Returns per rank a list of (window_index, branch) with branch in {"both", "uncond", "cond"}; the two branches of a
+    window that land on the same rank are fused into one "both" call."""
+    if not cfg:
+        per = [[] for _ in range(world)]
+        for k in range(n_windows):
+            per[k % world].append((k, "both"))
+        return per
+    units = [(cond_cost, k, "cond") for k in range(n_windows)] + [(1.0, k, "uncond") for k in range(n_windows)]
+    units.sort(key=lambda u: (-u[0], u[1]))
+    load = [0.0] * world
+    per = [[] for _ in range(world)]
+    for cost, k, br in units:
+        r = min(range(world), key=lambda i: (load[i], i))
+        load[r] += cost
+        per[r].append((k, br))
+    out = []
+    for lst in per:
+        wins = {}
+        for k, br in lst:
+            wins.setdefault(k, set()).add(br)
+        out.append(sorted((k, "both" if len(b) == 2 else next(iter(b))) for k, b in wins.items()))
+    return out
+
+
 def accumulate(acc: torch.Tensor, pred: torch.Tensor, window: List[int]):
     """CPU reference of ap_scatter_accumulate_f16: acc[b, window[f]] += pred[b, f] (acc fp32 [B, L, ...])."""
     for j, f in enumerate(window):

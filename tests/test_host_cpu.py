@@ -167,3 +167,22 @@ def test_window_sharding_world2_gloo():
         accumulate(acc, pred.permute(0, 2, 1, 3, 4), wd)
     ref = combine(acc, inv, 3.5)
     assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_plan_units_covers_every_window_branch_once_and_balances():
+    """(window, CFG branch) work units: every unit is assigned exactly once, every rank derives the same
+    plan, and 11 windows on 8 ranks balance better than whole windows (2 windows = 4.4 cost units on the busiest rank)."""
+    from aniportrait_b200.pipelines.sharding import plan_units
+    for n_windows, world in [(11, 8), (2, 2), (5, 4), (3, 8), (1, 2)]:
+        plan = plan_units(n_windows, True, world)
+        assert plan == plan_units(n_windows, True, world) and len(plan) == world
+        seen = []
+        for units in plan:
+            for k, br in units:
+                seen += [(k, "uncond"), (k, "cond")] if br == "both" else [(k, br)]
+        assert sorted(seen) == sorted([(k, b) for k in range(n_windows) for b in ("uncond", "cond")])
+    cost = {"both": 2.2, "cond": 1.2, "uncond": 1.0}
+    busiest = max(sum(cost[br] for _, br in units) for units in plan_units(11, True, 8))
+    assert busiest <= 3.45 < 4.4
+    # no CFG: whole windows round-robin
+    assert plan_units(3, False, 2) == [[(0, "both"), (2, "both")], [(1, "both")]]
