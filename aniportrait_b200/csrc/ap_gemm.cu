@@ -55,21 +55,31 @@ struct GemmParams {
                            // B / A load (traffic sensitivity); results are garbage
 };
 
-template <int BN, int CG = 1>
+// NACC = 2 ("wide" tile, cta_group::2 only): one staged A tile feeds TWO N = BN accumulators (two adjacent BN-wide weight
+// slabs), i.e. a 256 x 2BN output tile per CTA pair. Per 64-wide k-block and CTA the shared-memory port then moves
+// A 16 KB in + 2 x 16 KB out, B 20 KB in + 20 KB out = 88 KB per 640 MMA clocks instead of 2 x 52 KB (BN = 160), which is
+// what bounds the narrow tile. TMEM holds three BN-wide accumulator slots used in rotation (tile i:
+// slots 2i % 3 and (2i+1) % 3), so the epilogue of tile i still overlaps the mainloop of tile i+1 except for the drain
+// of its first slot.
+template <int BN, int CG = 1, int NACC = 1>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = (BN / CG) * BK * 2;   // cta_group::2: each CTA of the pair stages half of the B tile
+  static constexpr int B_SLAB = (BN / CG) * BK * 2;    // cta_group::2: each CTA of the pair stages half of a B slab
+  static constexpr int B_BYTES = NACC * B_SLAB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_STAGING = 8 * 4096;  // 8 epilogue warps x (2 KB output box + 2 KB residual box)
   static constexpr int MAX_SMEM = 227 * 1024 - 2048 - EPI_STAGING;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int ACC_SLOTS = NACC == 2 ? 3 : 2;
+  static constexpr int ACC_COLS = ACC_SLOTS * BN;
+  static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
-  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024B alignment");
+  static_assert(ACC_COLS <= 512, "the accumulator slots must fit TMEM");
+  static_assert(NACC == 1 || CG == 2, "wide tiles are built on cta_group::2");
+  static_assert(B_SLAB % 1024 == 0, "B stage must keep 1024B alignment");
 };
 
 // exact-erf GELU, erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below fp16 output resolution):
@@ -88,12 +98,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(0.5f * fabsf(x), erf_abs, 0.5f * x);     // 0.5 x (1 + sign(x) erf_abs)
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int NACC>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
             const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, NACC>;
   constexpr int STAGES = Cfg::STAGES;
   // CG == 2: the CTAs of a pair (cluster of 2) work on two vertically adjacent 128-row tiles with ONE M=256 MMA issued
   // by the leader (rank 0). `cta_rank` selects this CTA's A rows and its half of the B tile.
@@ -106,14 +116,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_STAGING);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;   // [8] one per epilogue warp
+  uint64_t* tmem_empty = tmem_full + 2;  // [3] one per accumulator slot (NACC == 1 uses two)
+  uint64_t* res_bar = tmem_empty + 3;   // [8] one per epilogue warp
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // work items: tiles (CG == 1) or pair-tiles of 2 x 128 rows (CG == 2); every CTA of a pair walks the same sequence
-  const int num_tiles = (p.num_m_tiles / CG) * p.num_n_tiles;
+  const int n_groups = p.num_n_tiles / NACC;   // NACC adjacent BN-wide weight slabs form one work item
+  const int num_tiles = (p.num_m_tiles / CG) * n_groups;
   const int first_tile = blockIdx.x / CG;
   const int tile_stride = gridDim.x / CG;
 
@@ -125,10 +136,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8 * CG);   // CG == 2: the leader's barrier collects both CTAs' epilogue warps
-    }
+    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1);
+    for (int s = 0; s < 3; ++s) mbar_init(&tmem_empty[s], 8 * CG);   // CG == 2: the leader collects both CTAs' warps
     for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     if (p.tma_epi) {
       tma_prefetch_desc(&tmOut);
@@ -153,8 +162,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
-        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = (tile / n_groups) * CG + (int)cta_rank;
+        const int n_tile = (tile % n_groups) * NACC;
         int n0 = 0, y0 = 0, x0 = 0;
         if (p.a_mode != A_GEMM) {
           const int per_frame = p.tiles_x * p.tiles_y;
@@ -197,9 +206,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               else tma_load_5d(am, &full_bar[stage], a_dst, px * p.C1 + c0, x0 + dx, py, y0 + dy, n0);
             }
             if (!load_b) {
-            } else if (CG == 2)
-              tma_load_2d_2sm(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN + (int)cta_rank * (BN / 2));
-            else
+            } else if (CG == 2) {
+#pragma unroll
+              for (int a = 0; a < NACC; ++a)
+                tma_load_2d_2sm(&tmB, &full_bar[stage], static_cast<uint8_t*>(b_dst) + a * Cfg::B_SLAB, kb * Cfg::BK,
+                                (n_tile + a) * BN + (int)cta_rank * (BN / 2));
+            } else
               tma_load_2d(&tmB, &full_bar[stage], b_dst, kb * Cfg::BK, n_tile * BN);
             }
           }
@@ -220,13 +232,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       constexpr uint32_t idesc = umma_idesc_f16(128 * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
       const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
-      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      uint32_t use0 = 0, use1 = 0, use2 = 0;   // completed uses of each accumulator slot (parity of its empty barrier)
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+        // accumulator slots of this work item: NACC == 1 ping-pongs 0 / 1, NACC == 2 rotates through three
+        const int s0 = NACC == 2 ? (int)((2 * it) % 3) : (int)(it & 1);
+        const int s1 = NACC == 2 ? (int)((2 * it + 1) % 3) : s0;
+        auto wait_slot = [&](int s) {
+          uint32_t& u = s == 0 ? use0 : (s == 1 ? use1 : use2);
+          mbar_wait(&tmem_empty[s], (u & 1) ^ 1);
+          ++u;
+        };
+        wait_slot(s0);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d0 = tmem_base + s0 * BN, d1 = tmem_base + s1 * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -237,21 +257,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < Cfg::BK / 16; ++k) {
               // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in the (>>4) start-address field
-              if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-              else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              if (CG == 2) umma_f16_ss_2sm(d0, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else umma_f16_ss(d0, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
+          }
+          if (NACC == 2) {
+            if (kb == 0) {   // the second slot belonged to the previous item's first half: wait for its drain only now
+              wait_slot(s1);
+              tc_fence_after();
+            }
+            const uint64_t db1 = umma_desc_k_sw128(b_base + stage * Cfg::B_BYTES + Cfg::B_SLAB);
+            if (elect_one()) {
+              if (p.debug != 2)
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k) umma_f16_ss_2sm(d1, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+            }
+          }
+          if (elect_one()) {
             if (CG == 2) {
-              umma_commit_2sm_mc(&empty_bar[stage], 3);                       // frees the stage in both CTAs
-              if (kb == p.num_kb - 1) umma_commit_2sm_mc(&tmem_full[acc], 3);  // wakes both CTAs' epilogues
+              umma_commit_2sm_mc(&empty_bar[stage], 3);                            // frees the stage in both CTAs
+              if (kb == p.num_kb - 1) umma_commit_2sm_mc(&tmem_full[it & 1], 3);    // wakes both CTAs' epilogues
             } else {
               umma_commit(&empty_bar[stage]);
-              if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+              if (kb == p.num_kb - 1) umma_commit(&tmem_full[it & 1]);
             }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -278,9 +311,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
       const int sw = (lane >> 1) & 3;                       // 64B-swizzle XOR term of this thread's row
       const int r0 = lane_group * 32;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
-        const int n_tile = tile % p.num_n_tiles;
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+        const int m_tile = (tile / n_groups) * CG + (int)cta_rank;
+        const int n_tile = (tile % n_groups) * NACC;
+        // accumulator slots of this work item (same rotation as the MMA issuer)
+        const int s0 = NACC == 2 ? (int)((2 * it) % 3) : (int)(it & 1);
+        const int s1 = NACC == 2 ? (int)((2 * it + 1) % 3) : s0;
         // coordinates of this warp's 32-row box
         int cy = 0, cx = 0, cn = 0;
         long long m = 0;
@@ -312,12 +349,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             else tma_load_4d(&tmRes, rbar, rbuf, col, cx, cy, cn);
           }
         };
-        if (has_res && col_half < NCHUNK) load_res(col_half);
+        if (has_res && col_half < NACC * NCHUNK) load_res(col_half);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(r0) << 16);
+        const uint32_t t_lanes = tmem_base + (static_cast<uint32_t>(r0) << 16);
+        bool released0 = false;
+        auto release = [&](int slot) {   // this warp is done reading accumulator slot `slot`
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(&tmem_empty[slot], 0);
+            else mbar_arrive(&tmem_empty[slot]);
+          }
+        };
 #pragma unroll 1
-        for (int c = col_half; c < NCHUNK; c += 2) {
+        for (int c = col_half; c < NACC * NCHUNK; c += 2) {
+          if (NACC == 2 && c >= NCHUNK && !released0) {   // first slot drained: the next item's second half may start
+            release(s0);
+            released0 = true;
+          }
+          const uint32_t t_row = t_lanes + (c < NCHUNK ? s0 : s1) * BN - (c < NCHUNK ? 0 : NCHUNK) * ACC_PER_CHUNK;
           const int acol = n_tile * BN + c * ACC_PER_CHUNK;       // first accumulator (weight-row) column
           float v[32];
           if (EPI == EPI_GEGLU) {
@@ -386,7 +437,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (has_res && c + 2 < NCHUNK) load_res(c + 2);      // rbuf fully consumed by every lane (syncwarp above)
+          if (has_res && c + 2 < NACC * NCHUNK) load_res(c + 2);      // rbuf fully consumed by every lane (syncwarp above)
           if (lane == 0) {
             const int ocol = n_tile * (BN / (EPI == EPI_GEGLU ? 2 : 1)) + c * 32;
             if (p.a_mode == A_GEMM) tma_store_2d(&tmOut, obuf, ocol, cy);
@@ -394,19 +445,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tma_store_commit();
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
-          else mbar_arrive(&tmem_empty[acc]);
-        }
+        if (NACC == 2 && !released0) release(s0);
+        release(s1);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) tma_store_wait_all<0>();   // stores must complete before the CTA (and its smem) goes away
     } else
-    for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-      const int m_tile = (tile / p.num_n_tiles) * CG + (int)cta_rank;
-      const int n_tile = tile % p.num_n_tiles;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {   // legacy direct-store epilogue (NACC == 1 only)
+      const int m_tile = (tile / n_groups) * CG + (int)cta_rank;
+      const int n_tile = tile % n_groups;
       // output row of this thread
       long long m;
       bool row_ok;
@@ -543,21 +590,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int NACC = 1>
 static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& to,
                        const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, NACC>;
   static bool attr_set = false;
   if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CG, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int items = (p.num_m_tiles / CG) * p.num_n_tiles;
+  const int items = (p.num_m_tiles / CG) * (p.num_n_tiles / NACC);
   const int max_ctas = (num_sms() / CG) * CG;
   const int grid = items * CG < max_ctas ? items * CG : max_ctas;
   if (CG == 1) {
-    gemm_kernel<BN, EPI, CG><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, to, tr, p);
+    gemm_kernel<BN, EPI, CG, NACC><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, to, tr, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -571,7 +618,7 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG>, a1, a2, b, to, tr, p));
+    AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG, NACC>, a1, a2, b, to, tr, p));
   }
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -598,6 +645,20 @@ static int pick_bn(int N, int forced, long long m_tiles, bool geglu = false) {
   return best;
 }
 
+// Wide (two-accumulator) tiles pay an exposed accumulator drain per work item, so they are used where the mainloop is
+// long (K >= 1920), the epilogue can use TMA, and the work still fills the chip at least as well as narrow tiles.
+static bool pick_wide(int bn, int epi, int cg, const GemmParams& p) {
+  static const int env = getenv("AP_GEMM_WIDE") ? atoi(getenv("AP_GEMM_WIDE")) : -1;   // 0 = never, 1 = whenever legal
+  if (env == 0) return false;
+  if (!(bn == 160 && epi == EPI_LINEAR && cg == 2 && p.tma_epi && p.num_n_tiles % 2 == 0)) return false;
+  if (env == 1) return true;
+  if (p.num_kb < 30) return false;
+  const long long pairs = num_sms() / 2;
+  const long long narrow = (long long)(p.num_m_tiles / 2) * p.num_n_tiles, wide = narrow / 2;
+  const long long t_narrow = (narrow + pairs - 1) / pairs, t_wide = 2 * ((wide + pairs - 1) / pairs);
+  return t_wide <= t_narrow;
+}
+
 static int dispatch(int bn, int epi, int cg, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,
                     const CUtensorMap& to, const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
 #define AP_CASE(BN_)                                                                     \
@@ -612,6 +673,7 @@ static int dispatch(int bn, int epi, int cg, const CUtensorMap& a1, const CUtens
     switch (bn) {
       AP_CASE2(256)
       case 160:
+        if (pick_wide(bn, epi, cg, p)) return launch_gemm<160, EPI_LINEAR, 2, 2>(a1, a2, b, to, tr, p, stream);
         return launch_gemm<160, EPI_LINEAR, 2>(a1, a2, b, to, tr, p, stream);
       AP_CASE2(128)
       default:
