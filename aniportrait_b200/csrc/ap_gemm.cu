@@ -645,14 +645,16 @@ static int pick_bn(int N, int forced, long long m_tiles, bool geglu = false) {
   return best;
 }
 
-// Wide (two-accumulator) tiles pay an exposed accumulator drain per work item, so they are used where the mainloop is
-// long (K >= 1920), the epilogue can use TMA, and the work still fills the chip at least as well as narrow tiles.
+// Wide (two-accumulator) tiles: used whenever the epilogue can use TMA and the work still fills the chip at least as well as
+// with narrow tiles. The exposed part of the accumulator drain made K < 320 the only losing case on the UNet's shapes
+// (whole-call replay 51.5 / 51.3 / 50.6 / 50.3 ms for a minimum of 30 / 20 / 10 / 5 k-blocks, same box).
 static bool pick_wide(int bn, int epi, int cg, const GemmParams& p) {
   static const int env = getenv("AP_GEMM_WIDE") ? atoi(getenv("AP_GEMM_WIDE")) : -1;   // 0 = never, 1 = whenever legal
   if (env == 0) return false;
   if (!(bn == 160 && epi == EPI_LINEAR && cg == 2 && p.tma_epi && p.num_n_tiles % 2 == 0)) return false;
   if (env == 1) return true;
-  if (p.num_kb < 30) return false;
+  static const int min_kb = getenv("AP_GEMM_WIDE_MINKB") ? atoi(getenv("AP_GEMM_WIDE_MINKB")) : 5;
+  if (p.num_kb < min_kb) return false;
   const long long pairs = num_sms() / 2;
   const long long narrow = (long long)(p.num_m_tiles / 2) * p.num_n_tiles, wide = narrow / 2;
   const long long t_narrow = (narrow + pairs - 1) / pairs, t_wide = 2 * ((wide + pairs - 1) / pairs);
