@@ -201,7 +201,7 @@ def kernel_rooflines(device, peaks):
     out = torch.empty(32, 64, 64, 320, device=device, dtype=torch.float16)
     ms = time_it(lambda: ops.conv3x3(x, wt, 320, bias=b, out=out))
     fl = 2.0 * 32 * 64 * 64 * 320 * 9 * 320
-    res["conv3x3"] = dict(kernel="gemm_kernel<BN=160,LINEAR,cta_group::2> (implicit-GEMM conv3x3 320->320 @64x64x32f)", ms=ms,
+    res["conv3x3"] = dict(kernel="gemm_kernel<BN=160,LINEAR,cta_group::2,NACC=2> (implicit-GEMM conv3x3 320->320 @64x64x32f, 256x320 tiles)", ms=ms,
                           tflops=fl / ms / 1e9)
     # (2) fused reference attention, 64x64 level: 32 frames (16 uncond: N keys, 16 cond: 2N keys), 8 heads, d=40
     n, heads, d, dpad, fr = 4096, 8, 40, 64, 32
