@@ -658,7 +658,9 @@ static bool pick_wide(int bn, int epi, int cg, const GemmParams& p) {
   const long long pairs = num_sms() / 2;
   const long long narrow = (long long)(p.num_m_tiles / 2) * p.num_n_tiles, wide = narrow / 2;
   const long long t_narrow = (narrow + pairs - 1) / pairs, t_wide = 2 * ((wide + pairs - 1) / pairs);
-  return t_wide <= t_narrow;
+  // a wide work item takes ~0.8x the time of the two narrow ones it replaces: accept up to `slack` % more wave-units
+  static const int slack = getenv("AP_GEMM_WIDE_SLACK") ? atoi(getenv("AP_GEMM_WIDE_SLACK")) : 25;
+  return t_wide * 100 <= t_narrow * (100 + slack);
 }
 
 static int dispatch(int bn, int epi, int cg, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b,

@@ -45,10 +45,22 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int
       }
     }
   }
-  extern __shared__ float2 sh[];  // [k][C] per-thread channel sums
+  extern __shared__ float2 sh[];  // [k][C] per-thread channel sums, then [C] channel totals
   if (rl < k) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) sh[rl * C + cv * 8 + j] = make_float2(s[j], q[j]);
+  }
+  __syncthreads();
+  // fixed-order tree: rows -> channel totals (all threads), channels -> groups (one thread per group)
+  float2* tot = sh + k * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float as = 0.f, aq = 0.f;
+    for (int r = 0; r < k; ++r) {
+      const float2 v = sh[r * C + c];
+      as += v.x;
+      aq += v.y;
+    }
+    tot[c] = make_float2(as, aq);
   }
   __syncthreads();
   const int g_lo = c_off / cpg, g_hi = (c_off + C - 1) / cpg;
@@ -56,12 +68,10 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int
     const int c0 = max(g * cpg, c_off) - c_off;
     const int c1 = min((g + 1) * cpg, c_off + C) - c_off;
     float as = 0.f, aq = 0.f;
-    for (int c = c0; c < c1; ++c)
-      for (int r = 0; r < k; ++r) {
-        const float2 v = sh[r * C + c];
-        as += v.x;
-        aq += v.y;
-      }
+    for (int c = c0; c < c1; ++c) {
+      as += tot[c].x;
+      aq += tot[c].y;
+    }
     partials[((long long)frame * gridDim.x + blockIdx.x) * G + g] = make_float2(as, aq);
   }
 }
@@ -374,9 +384,9 @@ extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int 
     gn_launch_geometry(HW, cs[s], Nf, &threads[s], &rpb[s], &chunks[s]);
     AP_REQUIRE((long long)chunks[s] * Nf <= AP_GN_MAX_BLOCKS, "groupnorm: %d frames exceed the partial-sum workspace", Nf);
     const int k = threads[s] / (cs[s] / 8);
-    AP_REQUIRE((size_t)k * cs[s] * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too wide for the reduction buffer", cs[s]);
+    AP_REQUIRE((size_t)(k + 1) * cs[s] * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too wide for the reduction buffer", cs[s]);
     if (s == 0) part[1] = part[0] + (long long)Nf * chunks[0] * groups;
-    gn_stats_kernel<<<dim3(chunks[s], Nf), threads[s], sizeof(float2) * k * cs[s], stream>>>(
+    gn_stats_kernel<<<dim3(chunks[s], Nf), threads[s], sizeof(float2) * (k + 1) * cs[s], stream>>>(
         (const __half*)srcs[s], HW, cs[s], offs[s], cpg, rpb[s], part[s], groups);
   }
   AP_CHECK_CUDA(cudaGetLastError());
