@@ -10,7 +10,8 @@ import re
 from ctypes import c_char_p, c_int, c_longlong, c_void_p, c_float, POINTER  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaniportrait_b200.so")
+# AP_LIB_PATH: load another build of the same library (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("AP_LIB_PATH") or os.path.join(_HERE, "libaniportrait_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aniportrait_b200.h")
 
 _lib = None
