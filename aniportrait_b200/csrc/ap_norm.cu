@@ -224,42 +224,47 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long rows, i
   }
 }
 
-// LayerNorm, wide-load variant for C % 64 == 0: 8 lanes per row (4 rows per warp), each lane keeps C/64 16-byte vectors of
-// its row in registers, so every load / store instruction moves 4 x 128 contiguous bytes (the one-warp-per-row kernel
-// above issues 4-byte accesses and reached 3.8 TB/s on 131072 x 320). Same exact two-pass statistics.
-template <int MAXV>  // MAXV >= C / 64
+// LayerNorm, wide-load variant for C % 8 == 0, C <= 1536: LPR lanes per row (32 / LPR rows per warp), each lane keeps up
+// to 6 16-byte vectors of its row in registers (vector v of the row belongs to lane v % LPR), so every load / store
+// instruction moves full 128-byte lines; LPR = 8 / 16 / 32 for C = 320 / 640 / 1280 keeps 5 vectors per lane at every
+// level (the one-warp-per-row kernel above issues 4-byte accesses; a fixed 8 lanes per row left the 1280-wide levels with
+// 20 vectors per lane, 128 registers and a quarter of the blocks). Same exact two-pass statistics.
+template <int LPR>
 __global__ void __launch_bounds__(256)
-layernorm8_kernel(const __half* __restrict__ x, long long rows, int C, float eps, const float* __restrict__ gamma,
+layernormv_kernel(const __half* __restrict__ x, long long rows, int C, float eps, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const float* __restrict__ pe, int rows_per_pe, int pe_period,
                   __half* __restrict__ y) {
+  constexpr int MAXV = 6;
+  constexpr int RPW = 32 / LPR;   // rows per warp
   const int lane = threadIdx.x & 31;
-  const int sub = lane & 7;
-  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const int sub = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
   const bool ok = row < rows;
-  const int nv = C >> 6;   // 16-byte vectors per lane
+  const int nvec = C >> 3;   // 16-byte vectors per row
   const uint4* src = reinterpret_cast<const uint4*>(x + (ok ? row : 0) * C);
   uint4 v[MAXV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-    if (i < nv) v[i] = ok ? __ldg(src + sub + 8 * i) : make_uint4(0u, 0u, 0u, 0u);
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = sub + LPR * i;
+    v[i] = (ok && vi < nvec) ? __ldg(src + vi) : make_uint4(0u, 0u, 0u, 0u);
+  }
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-    if (i < nv) {
-      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+  for (int i = 0; i < MAXV; ++i) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(h[t]);
-        sum += f.x + f.y;
-      }
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h[t]);
+      sum += f.x + f.y;           // vectors past the row end were zero-filled
     }
+  }
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / C;
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
-    if (i < nv) {
+    if (sub + LPR * i < nvec) {
       const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -269,15 +274,16 @@ layernorm8_kernel(const __half* __restrict__ x, long long rows, int C, float eps
       }
     }
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / C + eps);
   if (!ok) return;
   const float* pe_row = pe ? pe + (long long)((row / rows_per_pe) % pe_period) * C : nullptr;
   uint4* dst = reinterpret_cast<uint4*>(y + row * C);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-    if (i < nv) {
-      const int c0 = (sub + 8 * i) * 8;
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = sub + LPR * i;
+    if (vi < nvec) {
+      const int c0 = vi * 8;
       const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
@@ -299,8 +305,9 @@ layernorm8_kernel(const __half* __restrict__ x, long long rows, int C, float eps
       __half2* oh = reinterpret_cast<__half2*>(&u);
 #pragma unroll
       for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(o[2 * t], o[2 * t + 1]);
-      dst[sub + 8 * i] = u;
+      dst[vi] = u;
     }
+  }
 }
 
 // Row softmax (fp16 in/out, fp32 math) for the VAE's single-head 4096-token attention, which is evaluated as
@@ -423,17 +430,18 @@ extern "C" int ap_layernorm_f16(const void* x, long long rows, int C, float eps,
   AP_REQUIRE(C % 2 == 0 && C <= 64 * 32, "layernorm: C=%d unsupported (even, <= 2048)", C);
   AP_REQUIRE(pe == nullptr || (rows_per_pe > 0 && pe_period > 0), "layernorm: bad pe geometry");
   const int wpb = 8;
-  if (C % 64 == 0 && C / 64 <= 22 && getenv("AP_LAYERNORM_NARROW") == nullptr) {
-    const unsigned grid8 = (unsigned)((rows + 4 * wpb - 1) / (4 * wpb));
-    const int nv = C / 64;
-#define AP_LN8(MV)                                                                                                       \
-  layernorm8_kernel<MV><<<grid8, wpb * 32, 0, stream>>>((const __half*)x, rows, C, eps, gamma, beta, pe,                  \
-                                                        rows_per_pe > 0 ? rows_per_pe : 1, pe_period > 0 ? pe_period : 1, \
-                                                        (__half*)out)
-    if (nv <= 5) AP_LN8(5);
-    else if (nv <= 10) AP_LN8(10);
-    else AP_LN8(22);
-#undef AP_LN8
+  if (C % 8 == 0 && C / 8 <= 6 * 32 && getenv("AP_LAYERNORM_NARROW") == nullptr) {
+    const int nvec = C / 8;
+    const int lpr = nvec <= 6 * 8 ? 8 : (nvec <= 6 * 16 ? 16 : 32);
+    const unsigned gridv = (unsigned)((rows + (32 / lpr) * wpb - 1) / ((32 / lpr) * wpb));
+#define AP_LNV(L)                                                                                                        \
+  layernormv_kernel<L><<<gridv, wpb * 32, 0, stream>>>((const __half*)x, rows, C, eps, gamma, beta, pe,                   \
+                                                       rows_per_pe > 0 ? rows_per_pe : 1, pe_period > 0 ? pe_period : 1, \
+                                                       (__half*)out)
+    if (lpr == 8) AP_LNV(8);
+    else if (lpr == 16) AP_LNV(16);
+    else AP_LNV(32);
+#undef AP_LNV
     AP_CHECK_CUDA(cudaGetLastError());
     return AP_OK;
   }

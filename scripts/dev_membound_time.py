@@ -28,3 +28,8 @@ t("group_norm+silu 32x4096x320 (stats+apply)", lambda: ops.group_norm(x, g, b, 3
 x2 = x.view(-1, 320)
 y2 = torch.empty_like(x2)
 t("layer_norm 131072x320", lambda: ops.layer_norm(x2, g, b, out=y2), x.numel() * 4)
+for rows, c in [(32768, 640), (8192, 1280), (2048, 1280)]:
+    xx = torch.randn(rows, c, device=dev, dtype=torch.float16)
+    gg = torch.ones(c, device=dev); bb = torch.zeros(c, device=dev)
+    yy = torch.empty_like(xx)
+    t(f"layer_norm {rows}x{c}", lambda: ops.layer_norm(xx, gg, bb, out=yy), xx.numel() * 4)
