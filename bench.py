@@ -320,7 +320,10 @@ def run_product(args):
             "gpu_launches": launches,
             "phases_ms": {k: round(v, 3) for k, v in phases.items() if k.endswith("_ms")},
             "roofline": {"bound": "tensor", "achieved": round(roofs["conv3x3"]["tflops"], 2), "peak": peaks["tflops_burst"],
-                         "unit": "TFLOP/s", "frac": round(roofs["conv3x3"]["frac_of_peak"], 4), "traffic": None,
+                         "unit": "TFLOP/s", "frac": round(roofs["conv3x3"]["frac_of_peak"], 4),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape, from the
+                         # `ncu --set full` capture summarised in profiles/r01_ncu_full_top_kernels.md (not measured live)
+                         "traffic": 129.8e6, "traffic_unit": "bytes/launch (algorithmic 169.7e6: 84 in + 1.8 w + 84 out)",
                          "kernel": roofs["conv3x3"]["kernel"], "launch_ms": round(roofs["conv3x3"]["ms"], 4),
                          "peak_source": peaks["source"] + " burst (kernel timed alone)"},
             "roofline_ref_attention": {"bound": "tensor", "achieved": round(roofs["ref_attention"]["tflops"], 2),
