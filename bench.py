@@ -215,9 +215,28 @@ def kernel_rooflines(device, peaks):
     fl = 4.0 * n * d * heads * (16 * 2 * n + 16 * n)
     res["ref_attention"] = dict(kernel="attention5_kernel (ref-attn 64x64 level, d=40 padded to 64, 16 cond + 16 uncond frames)",
                                 ms=ms, tflops=fl / ms / 1e9)
-    # (3) one full UNet3D call is timed by the caller (aggregate)
+    # (3) temporal (frame-axis) attention of the motion modules at the 64x64 level: HBM-bound, 8*C bytes per token
+    B_, F_, N_, C_ = 2, 16, 4096, 320
+    tq = torch.randn(B_ * F_ * N_, 3 * C_, device=device, dtype=torch.float16)
+    to = torch.empty(B_ * F_ * N_, C_, device=device, dtype=torch.float16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > L2: every timed launch reads from HBM
+    for _ in range(2):
+        ops.temporal_attention(tq, B_, F_, N_, C_, 8, out=to)
+    tms = 0.0
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ops.temporal_attention(tq, B_, F_, N_, C_, 8, out=to)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tms += e0.elapsed_time(e1) / 5
+    nbytes = (tq.numel() + to.numel()) * 2
+    # (4) one full UNet3D call is timed by the caller (aggregate)
     for v in res.values():
         v["frac_of_peak"] = v["tflops"] / peaks["tflops_burst"]
+    res["temporal_attention"] = dict(kernel="temporal_attn_mma_kernel<40> (motion-module attention, 2x16 frames x 4096 positions x 320 ch)",
+                                     ms=tms, gbs=nbytes / tms / 1e6, frac_of_peak=nbytes / tms / 1e6 / peaks["hbm"])
     return res
 
 
@@ -332,6 +351,13 @@ def run_product(args):
                                        "kernel": roofs["ref_attention"]["kernel"],
                                        "launch_ms": round(roofs["ref_attention"]["ms"], 4),
                                        "note": "algorithmic FLOPs (d=40 unpadded; uncond frames N keys, cond frames 2N)"},
+            "roofline_temporal_attention": {"bound": "hbm", "achieved": round(roofs["temporal_attention"]["gbs"], 1),
+                                            "peak": peaks["hbm"], "unit": "GB/s",
+                                            "frac": round(roofs["temporal_attention"]["frac_of_peak"], 4),
+                                            "kernel": roofs["temporal_attention"]["kernel"],
+                                            "launch_ms": round(roofs["temporal_attention"]["ms"], 4),
+                                            "note": "algorithmic bytes: q,k,v read + out written once (335.5 MB); L2 flushed "
+                                                    "before every timed launch"},
             "roofline_unet_call": {"bound": "tensor", "achieved": round(unet_tflops, 2), "peak": peaks["tflops_sustained"],
                                    "unit": "TFLOP/s", "frac": round(unet_tflops / peaks["tflops_sustained"], 4),
                                    "ms": round(unet_ms, 3), "flop": FLOP_UNET_CALL,
