@@ -5,7 +5,8 @@ call) and a single `encode` of the reference image (once per video, :430-431).
   * `decode` on a CUDA fp16 model runs on the sm_100a kernels (channels-last, batched over frames): implicit-GEMM 3x3
     convs, fused GroupNorm+SiLU, tcgen05 GEMMs for the 1x1 shortcuts and the mid-block attention, which (single head,
     d = 512: too wide for the fused attention kernel's TMEM budget) is evaluated per frame as GEMM -> row-softmax -> GEMM.
-  * `encode` (once per video, off the per-step path) and any non-fp16 / non-CUDA use run as torch library ops.
+  * `encode` on a CUDA fp16 model takes the same kernels (the stride-2 downsamplers as stride-1 convolutions whose odd
+    outputs are gathered); any non-fp16 / non-CUDA use runs as torch library ops.
 """
 from __future__ import annotations
 
@@ -92,6 +93,61 @@ class _Stage(nn.Module):
         return x
 
 
+# ------------------------------------------------------------------------------------------------ kernel-path helpers
+def _pack_conv(c: nn.Conv2d):
+    w = ops.pack_conv3x3_weight(c.weight.detach())
+    b = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+    b[:c.out_channels] = f32(c.bias)
+    return w, b
+
+
+def _pack_res(r: "_Resnet"):
+    d = dict(g1=f32(r.norm1.weight), b1=f32(r.norm1.bias), g2=f32(r.norm2.weight), b2=f32(r.norm2.bias),
+             c1=_pack_conv(r.conv1), c2=_pack_conv(r.conv2), cout=r.conv1.out_channels)
+    if r.conv_shortcut is not None:
+        d["ws"] = f16(r.conv_shortcut.weight.reshape(r.conv_shortcut.out_channels, -1))
+        d["bs"] = f32(r.conv_shortcut.bias)
+    return d
+
+
+def _pack_attn(a: "_Attn"):
+    c = a.to_q.weight.shape[0]
+    scale = c ** -0.5
+    # softmax scale folded into the q projection; v bias folded into the output bias (softmax rows sum to 1):
+    # out = P.(xWv^T) Wo^T + (Wo bv + bo)
+    return dict(g=f32(a.group_norm.weight), b=f32(a.group_norm.bias), wq=f16(a.to_q.weight * scale),
+                bq=f32(a.to_q.bias * scale), wk=f16(a.to_k.weight), bk=f32(a.to_k.bias), wv=f16(a.to_v.weight),
+                wo=f16(a.to_out[0].weight), bo=f32(a.to_out[0].bias) + f32(a.to_out[0].weight) @ f32(a.to_v.bias), c=c)
+
+
+def _res_run(x, d, groups):
+    nf, h, w, cin = x.shape
+    hn = ops.group_norm(x, d["g1"], d["b1"], groups, 1e-6, True)
+    hc = ops.conv3x3(hn, d["c1"][0], d["cout"], bias=d["c1"][1])
+    hn2 = ops.group_norm(hc, d["g2"], d["b2"], groups, 1e-6, True)
+    res = ops.gemm(x.view(-1, cin), d["ws"], bias=d["bs"]).view(nf, h, w, d["cout"]) if "ws" in d else x
+    return ops.conv3x3(hn2, d["c2"][0], d["cout"], bias=d["c2"][1], residual=res)
+
+
+def _mid_attn_run(x, a, groups):
+    """Single-head mid-block attention (d = C = 512), one frame at a time: GEMM -> row softmax -> GEMM (the [tokens, tokens]
+    score matrix is 32 MB per frame at 512x512)."""
+    nf, h, w, c = x.shape
+    n = h * w
+    hn = ops.group_norm(x, a["g"], a["b"], groups, 1e-6, False).view(nf, n, c)
+    q = ops.gemm(hn.view(-1, c), a["wq"], bias=a["bq"]).view(nf, n, c)
+    k = ops.gemm(hn.view(-1, c), a["wk"], bias=a["bk"]).view(nf, n, c)
+    att = torch.empty(nf, n, c, dtype=torch.float16, device=x.device)
+    npad = (n + 31) // 32 * 32
+    for f in range(nf):
+        vt = ops.gemm(a["wv"], hn[f].contiguous())                   # V^T = Wv . X^T  [c, n]
+        sc = ops.gemm(q[f], k[f].contiguous() if npad == n else
+                      torch.cat([k[f], k[f].new_zeros(npad - n, c)]), n_valid=n)   # [n, n] scaled scores
+        ops.softmax_rows(sc)
+        ops.gemm(sc, vt, out=att[f])                                  # P . V   (K = n keys)
+    return ops.gemm(att.view(-1, c), a["wo"], bias=a["bo"], residual=x.view(-1, c)).view(nf, h, w, c)
+
+
 class Encoder(nn.Module):
     def __init__(self, cin, latent, boc, layers, groups):
         super().__init__()
@@ -111,6 +167,40 @@ class Encoder(nn.Module):
         for b in self.down_blocks:
             x = b(x)
         return self.conv_out(F.silu(self.conv_norm_out(self.mid_block(x))))
+
+    # ------------------------------------------------------------------------------------------ kernel path
+    def _packed(self):
+        if not hasattr(self, "_pk"):
+            self._pk = PackedCache()
+
+        def build():
+            return dict(conv_in=_pack_conv(self.conv_in),
+                        down=[dict(res=[_pack_res(r) for r in b.resnets],
+                                   down=_pack_conv(b.downsamplers[0].conv) if b._sampler == "down" else None)
+                              for b in self.down_blocks],
+                        mid=[_pack_res(r) for r in self.mid_block.resnets], attn=_pack_attn(self.mid_block.attentions[0]),
+                        gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)), conv_out=_pack_conv(self.conv_out))
+        return self._pk.get(self, build)
+
+    def run_nhwc(self, x: torch.Tensor, groups: int = 32) -> torch.Tensor:
+        """x: [Nf, H, W, 64] fp16 (3 image channels zero padded) -> moments [Nf, H/8, W/8, 2*latent] fp16.
+        diffusers' Downsample2D pads right/bottom by one and convolves with stride 2 and no padding:
+        out[o] = sum_k w[k] x[2o + k]. That is every other output of the ordinary stride-1, pad-1 convolution
+        (y[p] = sum_k w[k] x[p + k - 1], p = 2o + 1), which the implicit-GEMM kernel computes; the odd rows / columns are
+        then gathered (4x the FLOPs of three small layers instead of a dedicated asymmetric-padding mode)."""
+        pk = self._packed()
+        x = ops.conv3x3(x, pk["conv_in"][0], self.conv_in.out_channels, bias=pk["conv_in"][1])
+        for blk in pk["down"]:
+            for d in blk["res"]:
+                x = _res_run(x, d, groups)
+            if blk["down"] is not None:
+                y = ops.conv3x3(x, blk["down"][0], x.shape[-1], bias=blk["down"][1])
+                x = y[:, 1::2, 1::2, :].contiguous()
+        x = _res_run(x, pk["mid"][0], groups)
+        x = _mid_attn_run(x, pk["attn"], groups)
+        x = _res_run(x, pk["mid"][1], groups)
+        hn = ops.group_norm(x, pk["gn"][0], pk["gn"][1], groups, 1e-6, True)
+        return ops.conv3x3(hn, pk["conv_out"][0], self.conv_out.out_channels, bias=pk["conv_out"][1])
 
 
 class Decoder(nn.Module):
@@ -139,71 +229,26 @@ class Decoder(nn.Module):
         if not hasattr(self, "_pk"):
             self._pk = PackedCache()
 
-        def conv(c):
-            w = ops.pack_conv3x3_weight(c.weight.detach())
-            b = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
-            b[:c.out_channels] = f32(c.bias)
-            return w, b
-
-        def res(r):
-            d = dict(g1=f32(r.norm1.weight), b1=f32(r.norm1.bias), g2=f32(r.norm2.weight), b2=f32(r.norm2.bias),
-                     c1=conv(r.conv1), c2=conv(r.conv2), cout=r.conv1.out_channels)
-            if r.conv_shortcut is not None:
-                d["ws"] = f16(r.conv_shortcut.weight.reshape(r.conv_shortcut.out_channels, -1))
-                d["bs"] = f32(r.conv_shortcut.bias)
-            return d
-
         def build():
-            a = self.mid_block.attentions[0]
-            c = a.to_q.weight.shape[0]
-            scale = c ** -0.5
-            pk = dict(conv_in=conv(self.conv_in), mid=[res(r) for r in self.mid_block.resnets],
-                      attn=dict(g=f32(a.group_norm.weight), b=f32(a.group_norm.bias),
-                                # softmax scale folded into the q projection; v bias folded into the output bias
-                                # (softmax rows sum to 1): out = P.(xWv^T) Wo^T + (Wo bv + bo)
-                                wq=f16(a.to_q.weight * scale), bq=f32(a.to_q.bias * scale), wk=f16(a.to_k.weight),
-                                bk=f32(a.to_k.bias), wv=f16(a.to_v.weight), wo=f16(a.to_out[0].weight),
-                                bo=f32(a.to_out[0].bias) + f32(a.to_out[0].weight) @ f32(a.to_v.bias), c=c),
-                      up=[dict(res=[res(r) for r in b.resnets],
-                               up=conv(b.upsamplers[0].conv) if b._sampler == "up" else None) for b in self.up_blocks],
-                      gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)), conv_out=conv(self.conv_out))
-            return pk
+            return dict(conv_in=_pack_conv(self.conv_in), mid=[_pack_res(r) for r in self.mid_block.resnets],
+                        attn=_pack_attn(self.mid_block.attentions[0]),
+                        up=[dict(res=[_pack_res(r) for r in b.resnets],
+                                 up=_pack_conv(b.upsamplers[0].conv) if b._sampler == "up" else None)
+                            for b in self.up_blocks],
+                        gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)),
+                        conv_out=_pack_conv(self.conv_out))
         return self._pk.get(self, build)
-
-    @staticmethod
-    def _res_run(x, d, groups):
-        nf, h, w, cin = x.shape
-        hn = ops.group_norm(x, d["g1"], d["b1"], groups, 1e-6, True)
-        hc = ops.conv3x3(hn, d["c1"][0], d["cout"], bias=d["c1"][1])
-        hn2 = ops.group_norm(hc, d["g2"], d["b2"], groups, 1e-6, True)
-        res = ops.gemm(x.view(-1, cin), d["ws"], bias=d["bs"]).view(nf, h, w, d["cout"]) if "ws" in d else x
-        return ops.conv3x3(hn2, d["c2"][0], d["cout"], bias=d["c2"][1], residual=res)
 
     def run_nhwc(self, z: torch.Tensor, groups: int = 32) -> torch.Tensor:
         """z: [Nf, h, w, 64] fp16 (4 latent channels zero padded) -> [Nf, 8h, 8w, 3] fp16."""
         pk = self._packed()
         x = ops.conv3x3(z, pk["conv_in"][0], self.conv_in.out_channels, bias=pk["conv_in"][1])
-        x = self._res_run(x, pk["mid"][0], groups)
-        # mid-block attention, one frame at a time (the [tokens, tokens] score matrix is 32 MB per frame at 512x512)
-        a = pk["attn"]
-        nf, h, w, c = x.shape
-        n = h * w
-        hn = ops.group_norm(x, a["g"], a["b"], groups, 1e-6, False).view(nf, n, c)
-        q = ops.gemm(hn.view(-1, c), a["wq"], bias=a["bq"]).view(nf, n, c)
-        k = ops.gemm(hn.view(-1, c), a["wk"], bias=a["bk"]).view(nf, n, c)
-        att = torch.empty(nf, n, c, dtype=torch.float16, device=x.device)
-        npad = (n + 31) // 32 * 32
-        for f in range(nf):
-            vt = ops.gemm(a["wv"], hn[f].contiguous())                   # V^T = Wv . X^T  [c, n]
-            sc = ops.gemm(q[f], k[f].contiguous() if npad == n else
-                          torch.cat([k[f], k[f].new_zeros(npad - n, c)]), n_valid=n)   # [n, n] scaled scores
-            ops.softmax_rows(sc)
-            ops.gemm(sc, vt, out=att[f])                                  # P . V   (K = n keys)
-        x = ops.gemm(att.view(-1, c), a["wo"], bias=a["bo"], residual=x.view(-1, c)).view(nf, h, w, c)
-        x = self._res_run(x, pk["mid"][1], groups)
+        x = _res_run(x, pk["mid"][0], groups)
+        x = _mid_attn_run(x, pk["attn"], groups)
+        x = _res_run(x, pk["mid"][1], groups)
         for blk in pk["up"]:
             for d in blk["res"]:
-                x = self._res_run(x, d, groups)
+                x = _res_run(x, d, groups)
             if blk["up"] is not None:
                 x = ops.conv3x3(ops.upsample2x(x), blk["up"][0], x.shape[-1], bias=blk["up"][1])
         hn = ops.group_norm(x, pk["gn"][0], pk["gn"][1], groups, 1e-6, True)
@@ -252,6 +297,15 @@ class AutoencoderKL(ModelBase):
 
     @torch.no_grad()
     def encode(self, x, return_dict=True):
+        """x [n, 3, H, W] -> latent distribution. fp16 CUDA models with 64-multiple widths take the sm_100a kernel path
+        (set `kernel_encode = False` to force the torch modules)."""
+        if getattr(self, "kernel_encode", True) and self._kernel_decode_ok(x) and x.shape[1] <= 64 and x.shape[-1] % 64 == 0 \
+                and x.shape[-2] % 64 == 0:
+            n, c, h, w = x.shape
+            xp = torch.zeros(n, h, w, 64, dtype=torch.float16, device=x.device)
+            xp[..., :c] = x.permute(0, 2, 3, 1).to(torch.float16)
+            m = self.encoder.run_nhwc(xp, self.config.norm_num_groups).permute(0, 3, 1, 2)
+            return AutoencoderKLOutput(latent_dist=_LatentDist(self.quant_conv(m.to(self.quant_conv.weight.dtype))))
         return AutoencoderKLOutput(latent_dist=_LatentDist(self.quant_conv(self.encoder(x))))
 
     def _kernel_decode_ok(self, z):
