@@ -186,3 +186,26 @@ def test_plan_units_covers_every_window_branch_once_and_balances():
     assert busiest <= 3.45 < 4.4
     # no CFG: whole windows round-robin
     assert plan_units(3, False, 2) == [[(0, "both"), (2, "both")], [(1, "both")]]
+
+
+def test_ctypes_call_sites_match_the_header_prototypes():
+    """ABI drift guard: every `lib().ap_*(...)` call in aniportrait_b200/ops.py passes exactly as many arguments as the
+    prototype in include/aniportrait_b200.h declares (ctypes would not notice a missing / extra trailing argument)."""
+    import ast
+    import re
+    header = open(os.path.join(ROOT, "include", "aniportrait_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(ap_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    assert len(protos) >= 20
+    tree = ast.parse(open(os.path.join(ROOT, "aniportrait_b200", "ops.py")).read())
+    seen = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("ap_"):
+            seen[node.func.attr] = len(node.args)
+    assert seen, "no C-ABI call sites found in ops.py"
+    for name, n in seen.items():
+        assert name in protos, f"{name} is called from ops.py but not declared in the header"
+        assert n == protos[name], f"{name}: ops.py passes {n} arguments, the header declares {protos[name]}"
