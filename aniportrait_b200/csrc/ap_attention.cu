@@ -11,7 +11,11 @@
 // forward of ReferenceAttentionControl (reference src/models/mutual_self_attention.py:147-186; plain blocks
 // src/models/attention.py:323-330, write mode :137-146; PoseGuider's self-attention src/models/pose_guider.py:86-89).
 //
-// Persistent CTAs over (frame, head, 128-query tile) work units; 6 warps:
+// Three kernel generations share this file (dispatch in ap_attention_f16; measurements in profiles/):
+//   attention_kernel   (v1)  d <= 192 or <= 128 tokens: the structure described next
+//   attention3_kernel  (v3)  d <= 128: two query tiles per CTA, P kept in TMEM
+//   attention5_kernel  (v5)  d <= 64 (the 64x64 level, 88 % of the FLOPs): one query tile per CTA, two CTAs per SM
+// v1: persistent CTAs over (frame, head, 128-query tile) work units; 6 warps:
 //   warp 0     TMA producer: Q tile once per unit, K/V tiles through an mbarrier ring (own rows, then bank rows)
 //   warp 1     MMA issuer:   S = Q.K^T (accumulator double-buffered in TMEM), O += P.V (P from smem, V MN-major)
 //   warps 2-5  softmax + epilogue: thread = query row; S row held in registers; base-2 online softmax with lazy

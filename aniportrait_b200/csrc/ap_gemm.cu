@@ -4,9 +4,15 @@
 //
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier full/empty)
-//   warp 1      MMA issuer    (tcgen05.mma cta_group::1, M=128, N=BN, K=16; accumulators double-buffered in TMEM)
-//   warps 2..9  epilogue      (tcgen05.ld -> +bias, +residual | GEGLU -> fp16 -> global), overlaps next tile's mainloop;
-//               two warps per TMEM lane quarter, each taking every other 32-column chunk
+//   warp 1      MMA issuer    (tcgen05.mma, M=128, N=BN, K=16; accumulators double-buffered in TMEM)
+//   warps 2..9  epilogue      (tcgen05.ld -> +bias, +residual | GEGLU -> fp16 -> swizzled smem box -> TMA store), overlaps
+//               the next tile's mainloop; two warps per TMEM lane quarter, each taking every other 32-column chunk
+// Template variants (chosen per problem by pick_bn / pick_cg / pick_wide):
+//   CG = 2      the CTAs of a 2-CTA cluster take two vertically adjacent 128-row tiles; ONE tcgen05.mma cta_group::2 (M=256)
+//               issued by the leader consumes a B tile of which each CTA staged half
+//   NACC = 2    "wide" tile on top of CG = 2: one staged A tile feeds two N=BN accumulators (256 x 2BN outputs per pair),
+//               three TMEM slots in rotation. The kernel is bound by the SM's shared-memory port (operand reads + TMA
+//               writes), not by the tensor pipe: DESIGN.md section 4.
 //
 // The A operand is fetched by TMA in one of three addressing modes, so that linear layers, 1x1 convs, 3x3 convs
 // (stride 1 and 2, zero padding via TMA out-of-bounds fill) and channel-concatenated inputs (two K sources) share
