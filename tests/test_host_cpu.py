@@ -209,3 +209,31 @@ def test_ctypes_call_sites_match_the_header_prototypes():
     for name, n in seen.items():
         assert name in protos, f"{name} is called from ops.py but not declared in the header"
         assert n == protos[name], f"{name}: ops.py passes {n} arguments, the header declares {protos[name]}"
+
+
+def test_short_pipelines_forward_to_the_shared_core_with_single_window_arguments():
+    """pipeline_pose2vid / pipeline_pose2img are thin wrappers: the whole clip is ONE window (context_frames = L, no
+    overlap), the CLIP input is not squashed, clips longer than the temporal PE table are rejected, and the image pipeline is
+    a one-frame clip whose result is exposed as `.images`."""
+    from unittest import mock
+    from aniportrait_b200.pipelines import pipeline_pose2img, pipeline_pose2vid
+    from aniportrait_b200.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline as Long
+    calls = []
+
+    def fake_call(self, *args, **kwargs):
+        calls.append((args, kwargs))
+        return "VIDEO" if kwargs.get("return_dict", args[12] if len(args) > 12 else True) else "RAW"
+
+    with mock.patch.object(Long, "__call__", fake_call):
+        short = pipeline_pose2vid.Pose2VideoPipeline.__new__(pipeline_pose2vid.Pose2VideoPipeline)
+        out = short("ref", ["p"] * 20, "refpose", 512, 512, 20, 25, 3.5)
+        args, kw = calls[-1]
+        assert out == "VIDEO" and args[5] == 20
+        assert kw["context_frames"] == 20 and kw["context_overlap"] == 0 and kw["clip_resize"] is False
+        with pytest.raises(ValueError):
+            short("ref", ["p"] * 40, "refpose", 512, 512, 40, 25, 3.5)
+        img = pipeline_pose2img.Pose2ImagePipeline.__new__(pipeline_pose2img.Pose2ImagePipeline)
+        res = img("ref", "pose", "refpose", 512, 512, 25, 3.5)
+        args, kw = calls[-1]
+        assert args[1] == ["pose"] and args[5] == 1 and kw["context_frames"] == 1
+        assert isinstance(res, pipeline_pose2img.Pose2ImagePipelineOutput) and res.images == "RAW"
