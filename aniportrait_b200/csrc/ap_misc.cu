@@ -438,6 +438,9 @@ __global__ void gather_window_kernel(const __half* __restrict__ lat, const int* 
 }
 
 // acc[b, idx[f], px, :] += pred[(b, f), px, 0..4)   (fp32 accumulation of overlapping windows)
+// A window that holds the same frame twice (dilated windows wrapping around a short clip) contributes that frame ONCE, from
+// its last occurrence — the semantics of the reference's index assignment noise_pred[:, :, c] = noise_pred[:, :, c] + pred
+// (pipeline_pose2vid_long.py:546-547), and race-free.
 __global__ void scatter_accumulate_kernel(const __half* __restrict__ pred, int ld, const int* __restrict__ idx,
                                           float* __restrict__ acc, int B, int F, int L, int HW) {
   const long long total = (long long)B * F * HW;
@@ -446,17 +449,22 @@ __global__ void scatter_accumulate_kernel(const __half* __restrict__ pred, int l
   const int px = (int)(t % HW);
   const int f = (int)((t / HW) % F);
   const int b = (int)(t / ((long long)HW * F));
+  const int frame = idx[f];
+  for (int g = f + 1; g < F; ++g)
+    if (idx[g] == frame) return;
   const __half* s = pred + t * ld;
-  float4* d = reinterpret_cast<float4*>(acc + (((long long)b * L + idx[f]) * HW + px) * 4);
+  float4* d = reinterpret_cast<float4*>(acc + (((long long)b * L + frame) * HW + px) * 4);
   float4 a = *d;
   a.x += __half2float(s[0]); a.y += __half2float(s[1]); a.z += __half2float(s[2]); a.w += __half2float(s[3]);
   *d = a;
 }
 
 // noise = acc / count ; CFG: u + g (c - u) ; DDIM v-prediction step (eta = 0) ; latents updated in place; acc zeroed.
+// x0 = c_xx x + c_xv v, eps = c_ex x + c_ev v (the three diffusers prediction types differ only in these coefficients),
+// optional clamp of x0 (clip_sample; eps is NOT recomputed: use_clipped_model_output = False), then the eta = 0 update.
 __global__ void cfg_ddim_step_kernel(float* __restrict__ acc, const float* __restrict__ inv_count, int cfg, float guidance,
-                                     float sqrt_at, float sqrt_bt, float sqrt_ap, float sqrt_bp,
-                                     __half* __restrict__ lat, int L, int HW) {
+                                     float c_xx, float c_xv, float c_ex, float c_ev, float clip, float sqrt_ap,
+                                     float sqrt_bp, __half* __restrict__ lat, int L, int HW) {
   const long long total = (long long)L * HW * 4;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -473,8 +481,9 @@ __global__ void cfg_ddim_step_kernel(float* __restrict__ acc, const float* __res
   }
   acc[t] = 0.f;
   const float x = __half2float(lat[t]);
-  const float x0 = sqrt_at * x - sqrt_bt * v;
-  const float eps = sqrt_at * v + sqrt_bt * x;
+  float x0 = c_xx * x + c_xv * v;
+  const float eps = c_ex * x + c_ev * v;
+  if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
   lat[t] = __float2half_rn(sqrt_ap * x0 + sqrt_bp * eps);
 }
 
@@ -609,11 +618,25 @@ extern "C" int ap_scatter_accumulate_f16(const void* pred, int ld, const int* fr
 }
 
 extern "C" int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg, float guidance, float alpha_t,
-                                    float alpha_prev, void* latents, int L, int HW, void* stream) {
+                                    float alpha_prev, int prediction_type, float clip_range, void* latents, int L, int HW,
+                                    void* stream) {
   AP_REQUIRE(acc && inv_count && latents, "cfg_ddim_step: null pointer");
+  const float sa = sqrtf(alpha_t), sb = sqrtf(1.f - alpha_t);
+  float c_xx, c_xv, c_ex, c_ev;
+  if (prediction_type == AP_PRED_V) {
+    c_xx = sa; c_xv = -sb; c_ex = sb; c_ev = sa;
+  } else if (prediction_type == AP_PRED_EPSILON) {
+    AP_REQUIRE(alpha_t > 0.f, "cfg_ddim_step: epsilon prediction needs alpha_t > 0");
+    c_xx = 1.f / sa; c_xv = -sb / sa; c_ex = 0.f; c_ev = 1.f;
+  } else if (prediction_type == AP_PRED_SAMPLE) {
+    AP_REQUIRE(alpha_t < 1.f, "cfg_ddim_step: sample prediction needs alpha_t < 1");
+    c_xx = 0.f; c_xv = 1.f; c_ex = 1.f / sb; c_ev = -sa / sb;
+  } else {
+    return ap::fail(AP_ERR_INVALID, "cfg_ddim_step: unknown prediction_type %d", prediction_type);
+  }
   const long long total = (long long)L * HW * 4;
   cfg_ddim_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      acc, inv_count, cfg, guidance, sqrtf(alpha_t), sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev),
+      acc, inv_count, cfg, guidance, c_xx, c_xv, c_ex, c_ev, clip_range, sqrtf(alpha_prev), sqrtf(1.f - alpha_prev),
       (__half*)latents, L, HW);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;

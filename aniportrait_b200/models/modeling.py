@@ -24,6 +24,9 @@ class ModelBase(nn.Module):
     scripts/pose2vid.py:59-110 and pipeline_pose2vid_long.py:408,444)."""
 
     config_name = "config.json"
+    # substrings of state-dict keys that from_pretrained() tolerates as absent from / unknown to the checkpoint
+    _allow_missing_keys = ()
+    _allow_unexpected_keys = ()
 
     def register_to_config(self, **kwargs):
         self.__dict__["_internal_dict"] = FrozenDict(kwargs)
@@ -72,7 +75,7 @@ class ModelBase(nn.Module):
             sd = torch.load(pt, map_location="cpu", weights_only=True)
         else:
             raise FileNotFoundError(f"no weights file found in {path}")
-        model.load_state_dict(sd, strict=False)
+        load_checked(model, sd, cls._allow_missing_keys, cls._allow_unexpected_keys)
         return model
 
     @classmethod
@@ -81,6 +84,44 @@ class ModelBase(nn.Module):
         init = {k: v for k, v in dict(config).items() if k in sig and not k.startswith("_")}
         init.update({k: v for k, v in kwargs.items() if k in sig})
         return cls(**init)
+
+
+# diffusers < 0.19 checkpoints (sd-vae-ft-mse as published) name the VAE mid-block attention query/key/value/proj_attn;
+# diffusers 0.24 remaps them in ModelMixin._convert_deprecated_attention_blocks [dep]. Same remap here.
+_LEGACY_ATTENTION_KEYS = (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0"))
+
+
+def remap_legacy_attention_keys(state_dict: dict, target_keys) -> dict:
+    out = {}
+    target_keys = set(target_keys)
+    for k, v in state_dict.items():
+        nk = k
+        if k not in target_keys:
+            for old, new in _LEGACY_ATTENTION_KEYS:
+                for leaf in ("weight", "bias"):
+                    if k.endswith(f".{old}.{leaf}"):
+                        cand = k[: -len(f"{old}.{leaf}")] + f"{new}.{leaf}"
+                        if cand in target_keys:
+                            nk = cand
+        out[nk] = v
+    return out
+
+
+def load_checked(model: nn.Module, state_dict: dict, allow_missing=(), allow_unexpected=()):
+    """load_state_dict that does not fail silently: legacy attention names are remapped, and any key that is missing from the
+    checkpoint or unknown to the model raises unless it matches one of the allowed substrings (e.g. "motion_modules." when
+    the 2-D SD1.5 weights are loaded into the 3-D UNet before the motion-module file is merged)."""
+    own = model.state_dict().keys()
+    sd = remap_legacy_attention_keys(state_dict, own)
+    res = model.load_state_dict(sd, strict=False)
+    missing = [k for k in res.missing_keys if not any(a in k for a in allow_missing)]
+    unexpected = [k for k in res.unexpected_keys if not any(a in k for a in allow_unexpected)]
+    if missing or unexpected:
+        def head(keys):
+            return ", ".join(keys[:6]) + (f", ... (+{len(keys) - 6})" if len(keys) > 6 else "")
+        raise RuntimeError(f"{type(model).__name__}: checkpoint does not match the model: "
+                           f"{len(missing)} missing [{head(missing)}]; {len(unexpected)} unexpected [{head(unexpected)}]")
+    return res
 
 
 class PackedCache:

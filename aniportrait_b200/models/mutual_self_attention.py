@@ -38,6 +38,7 @@ class ReferenceAttentionControl:
                 m._ref_mode = mode
                 m._ref_cfg = bool(do_classifier_free_guidance)
                 m._bank_kv = None
+                m._attn2_const = None
 
     def _modules(self, unet, types=(BasicTransformerBlock, TemporalBasicTransformerBlock)):
         if self.fusion_blocks == "midup":
@@ -55,6 +56,7 @@ class ReferenceAttentionControl:
         for r, w in zip(readers, writers):
             r.bank = [v.clone().to(dtype) for v in w.bank]
             r._bank_kv = None
+            r._attn2_const = None
 
     def clear(self):
         if not self.reference_attn:
@@ -62,3 +64,4 @@ class ReferenceAttentionControl:
         for m in self._modules(self.unet):
             m.bank.clear()
             m._bank_kv = None
+            m._attn2_const = None

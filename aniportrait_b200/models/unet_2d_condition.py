@@ -72,6 +72,10 @@ class UNetMidBlock2DCrossAttn(nn.Module):
 
 
 class UNet2DConditionModel(ModelBase):
+    # the SD1.5 checkpoint the scripts load first (scripts/pose2vid.py:62-65) still carries the output head the
+    # ReferenceNet does not have (reference unet_2d_condition.py:645-655)
+    _allow_unexpected_keys = ("conv_out.", "conv_norm_out.")
+
     def __init__(self, sample_size: Optional[int] = None, in_channels: int = 4, out_channels: int = 4,
                  center_input_sample: bool = False, flip_sin_to_cos: bool = True, freq_shift: int = 0,
                  down_block_types: Tuple[str] = ("CrossAttnDownBlock2D", "CrossAttnDownBlock2D",

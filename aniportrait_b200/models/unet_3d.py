@@ -18,7 +18,7 @@ from torch import nn
 
 from .. import ops
 from .blocks import (Downsample, ResnetBlock, RunCtx, Transformer3DModel, Upsample, VanillaTemporalModule)
-from .modeling import ModelBase, PackedCache, f16, f32
+from .modeling import ModelBase, PackedCache, f16, f32, load_checked
 
 
 @dataclass
@@ -206,7 +206,7 @@ class UNet3DConditionModel(ModelBase):
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward_nhwc(self, x: torch.Tensor, batch: int, frames: int, timestep, encoder_hidden_states,
-                     pose_nhwc=None, ref_branch=None) -> torch.Tensor:
+                     pose_nhwc=None, ref_branch=None, ehs_key=None) -> torch.Tensor:
         """x: [(batch frames), H, W, 64] fp16 (4 latent channels zero padded to 64). pose_nhwc: 5 maps, each
         [(batch frames) | frames, h, w, C] (a [frames,...] map is shared by all CFG branches).
         Returns [(batch frames), H, W, out_channels] fp16."""
@@ -223,7 +223,7 @@ class UNet3DConditionModel(ModelBase):
         t_emb = ops.timestep_embedding(t.contiguous(), self.conv_in.out_channels)
         emb = self.time_embedding.run(t_emb)
         ehs = encoder_hidden_states.to(torch.float16).contiguous() if encoder_hidden_states is not None else None
-        ctx = RunCtx(batch, frames, ops.silu(emb), ehs, ehs_key=None, ref_branch=ref_branch)   # see RunCtx
+        ctx = RunCtx(batch, frames, ops.silu(emb), ehs, ehs_key=ehs_key, ref_branch=ref_branch)   # see RunCtx
 
         def add_pose(x, k):
             if pose_nhwc is None:
@@ -251,13 +251,15 @@ class UNet3DConditionModel(ModelBase):
         hn = ops.group_norm(x, pk["gn"], pk["bn"], self.groups, self.eps, True)
         return ops.conv3x3(hn, pk["wo"], self.conv_out.out_channels, bias=pk["bo"])
 
-    def prepare_reference(self, batch: int, frames: int, encoder_hidden_states):
+    def prepare_reference(self, batch: int, frames: int, encoder_hidden_states, ehs_key=None, ref_branch=None):
         """Once per video, before the denoising loop: every reader block projects its ReferenceNet bank to K/V and
         evaluates its (query-independent) attn2 constant, so that the per-step forward — typically replayed from a CUDA
         graph — contains none of this step-invariant work."""
         from .blocks import BasicTransformerBlock
         ehs = encoder_hidden_states.to(torch.float16).contiguous()
-        ctx = RunCtx(batch, frames, None, ehs, ehs_key=None)
+        if ehs_key is None:
+            raise ValueError("prepare_reference needs an explicit ehs_key (the identity of this video's conditioning)")
+        ctx = RunCtx(batch, frames, None, ehs, ehs_key=ehs_key, ref_branch=ref_branch)
         for m in self.modules():
             if isinstance(m, BasicTransformerBlock):
                 m.prepare(ctx)
@@ -326,5 +328,9 @@ class UNet3DConditionModel(ModelBase):
             if mm_zero_proj_out:
                 motion_state_dict = OrderedDict((k, v) for k, v in motion_state_dict.items() if "proj_out" not in k)
             state_dict.update(motion_state_dict)
-        model.load_state_dict(state_dict, strict=False)
+        # the reference loads with strict=False and prints the counts (unet_3d.py:663-673); here everything except the
+        # motion-module keys (absent when no motion file is given, or proj_out dropped by mm_zero_proj_out) and the
+        # position-encoding buffers must be present, and nothing unknown may be in the files
+        load_checked(model, state_dict, allow_missing=("motion_modules.", ".pos_encoder.pe"),
+                     allow_unexpected=(".pos_encoder.pe",))
         return model

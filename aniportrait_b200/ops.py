@@ -364,13 +364,20 @@ def scatter_accumulate(pred: torch.Tensor, frame_idx: torch.Tensor, acc: torch.T
     _count()
 
 
+PREDICTION_TYPES = {"v_prediction": 0, "epsilon": 1, "sample": 2}   # AP_PRED_* in include/aniportrait_b200.h
+
+
 def cfg_ddim_step(acc: torch.Tensor, inv_count: torch.Tensor, guidance: float, alpha_t: float, alpha_prev: float,
-                  latents: torch.Tensor):
-    """In place: latents <- DDIM v-prediction step of the CFG-combined, overlap-averaged prediction; acc zeroed."""
+                  latents: torch.Tensor, prediction_type: str = "v_prediction", clip_range: float = 0.0):
+    """In place: latents <- DDIM (eta = 0) step of the CFG-combined, overlap-averaged prediction; acc zeroed.
+    clip_range > 0 clamps the predicted x0 (DDIMScheduler clip_sample)."""
+    if prediction_type not in PREDICTION_TYPES:
+        raise ValueError(f"prediction_type {prediction_type!r} is not one of {sorted(PREDICTION_TYPES)}")
     _ensure(latents)
     B, L, h, w, _ = acc.shape
     assert latents.shape == (L, h, w, 4) and latents.dtype == torch.float16 and inv_count.dtype == torch.float32
     check(lib().ap_cfg_ddim_step_f16(fptr(acc), fptr(inv_count), I(1 if B == 2 else 0), _lib.c_float(guidance),
-                                     _lib.c_float(alpha_t), _lib.c_float(alpha_prev), ptr(latents), I(L), I(h * w),
-                                     stream_ptr()), "ap_cfg_ddim_step_f16")
+                                     _lib.c_float(alpha_t), _lib.c_float(alpha_prev),
+                                     I(PREDICTION_TYPES[prediction_type]), _lib.c_float(clip_range), ptr(latents),
+                                     I(L), I(h * w), stream_ptr()), "ap_cfg_ddim_step_f16")
     _count()

@@ -28,6 +28,10 @@ def uniform(step: int = 0, num_steps: Optional[int] = None, num_frames: int = 0,
     end = num_frames + shift - (0 if closed_loop else context_overlap)
     for level in range(levels):
         hop = 1 << level                                   # frame spacing inside a window at this level
+        if context_size * hop - context_overlap == 0:
+            raise ValueError("range() arg 3 must not be zero")     # what the reference's range(...) raises (context.py:36-40)
+        if context_size * hop - context_overlap < 0:
+            continue                                       # negative range step: the reference yields nothing at this level
         origin = int(frac * hop) + shift
         while origin < end:
             yield [(origin + k * hop) % num_frames for k in range(context_size)]

@@ -50,6 +50,7 @@ class Pose2VideoPipelineOutput:
 
 class Pose2VideoPipeline:
     _optional_components = []
+    _video_counter = 0
 
     def __init__(self, vae, image_encoder, reference_unet, denoising_unet, pose_guider, scheduler,
                  image_proj_model=None, tokenizer=None, text_encoder=None):
@@ -149,20 +150,56 @@ class Pose2VideoPipeline:
             return u8.permute(0, 3, 1, 2).to(torch.float32) * 2.0 - 1.0
         return torch.cat([self.cond_image_processor.preprocess(p, height=height, width=width) for p in frames], dim=0)
 
-    def _broadcast_banks(self, writer, device):
-        """NCCL broadcast (rank 0 -> all) of the ReferenceNet banks: 16 tensors [dup, N, C] fp16, ~46 MB at 512x512."""
+    def _bank_layout(self, S):
+        """Shapes of the 16 ReferenceNet banks in writer order. Rank 0 knows them after its write pass; the other ranks learn
+        them ONCE per session geometry (a few integers), so that every later video needs exactly one data broadcast."""
+        device = S.lat.device
+        mods = S.writer._modules(S.writer.unet)
         rank = torch.distributed.get_rank()
-        for m in writer._modules(writer.unet):
-            if rank == 0:
-                t = m.bank[0].contiguous()
-                shape = torch.tensor(list(t.shape), device=device)
-            else:
-                shape = torch.zeros(3, dtype=torch.long, device=device)
-            torch.distributed.broadcast(shape, 0)
-            if rank != 0:
-                t = torch.empty(*[int(v) for v in shape], dtype=torch.float16, device=device)
-            torch.distributed.broadcast(t, 0)
-            m.bank = [t]
+        if rank == 0:
+            meta = torch.tensor([list(m.bank[0].shape) for m in mods], dtype=torch.long, device=device).reshape(-1)
+        else:
+            meta = torch.zeros(3 * len(mods), dtype=torch.long, device=device)
+        torch.distributed.broadcast(meta, 0)
+        return [tuple(int(v) for v in meta[3 * i:3 * i + 3]) for i in range(len(mods))]
+
+    def _pack_banks(self, S):
+        """Rank 0, after the write pass: the banks into the session's ONE flat fp16 buffer (46 MB at 512x512)."""
+        off = 0
+        for m, shp in zip(S.writer._modules(S.writer.unet), S.bank_shapes):
+            n = shp[0] * shp[1] * shp[2]
+            S.bank_flat[off:off + n].copy_(m.bank[0].reshape(-1))
+            off += n
+
+    def _unpack_banks(self, S):
+        """Every rank, after the broadcast: the writer blocks' banks become views of the flat buffer."""
+        off = 0
+        for m, shp in zip(S.writer._modules(S.writer.unet), S.bank_shapes):
+            n = shp[0] * shp[1] * shp[2]
+            m.bank = [S.bank_flat[off:off + n].view(*shp)]
+            off += n
+
+    def _scheduler_update_rule(self):
+        """(prediction_type, clip_range) of the scheduler's DDIM update, validated against what the fused CFG + DDIM kernel
+        implements (diffusers DDIMScheduler.step with eta = 0). Anything else raises instead of silently producing wrong
+        latents (configs/inference/inference_v2.yaml:24-33 is v_prediction without clipping; inference_v1.yaml epsilon)."""
+        cfgd = getattr(self.scheduler, "config", None)
+
+        def get(name, default):
+            if cfgd is None:
+                return default
+            if isinstance(cfgd, dict):
+                return cfgd.get(name, default)
+            return getattr(cfgd, name, default)
+        pred_type = get("prediction_type", "epsilon")
+        if pred_type not in ops.PREDICTION_TYPES:
+            raise NotImplementedError(f"scheduler prediction_type {pred_type!r} is not supported by the fused DDIM step")
+        if get("thresholding", False):
+            raise NotImplementedError("dynamic thresholding is not supported by the fused DDIM step")
+        if not (hasattr(self.scheduler, "alpha_pair") or hasattr(self.scheduler, "alphas_cumprod")):
+            raise NotImplementedError(f"{type(self.scheduler).__name__} is not a DDIM-style scheduler (no alphas_cumprod)")
+        clip_range = float(get("clip_sample_range", 1.0)) if get("clip_sample", False) else 0.0
+        return pred_type, clip_range
 
     def _alpha_pair(self, t: int):
         if hasattr(self.scheduler, "alpha_pair"):
@@ -200,12 +237,18 @@ class Pose2VideoPipeline:
         for idx in S.win_idx_long:
             fea = self.pose_guider.forward_nhwc(S.pose_cond.index_select(0, idx))
             S.win_pose.append([f.to(torch.float16).contiguous() for f in fea])
-        self.denoising_unet.prepare_reference(S.dup, S.frames0, S.ehs)
+        branches = {br for _, br in S.units} or {"both"}
+        if "both" in branches:
+            self.denoising_unet.prepare_reference(S.dup, S.frames0, S.ehs, ehs_key=S.video_key)
+        for b, br in enumerate(("uncond", "cond")):       # single-branch (batch-1) units of a CFG reader
+            if br in branches:
+                self.denoising_unet.prepare_reference(1, S.frames0, S.ehs[b:b + 1], ehs_key=S.video_key, ref_branch=br)
 
     def _window_step(self, S, k):
         idx = S.win_idx[k]
         x = ops.gather_window(S.lat, idx, S.dup, 64)
-        pred = self.denoising_unet.forward_nhwc(x, S.dup, idx.numel(), S.t_dev, S.ehs, S.win_pose[k])
+        pred = self.denoising_unet.forward_nhwc(x, S.dup, idx.numel(), S.t_dev, S.ehs, S.win_pose[k],
+                                                ehs_key=S.video_key)
         ops.scatter_accumulate(pred, idx, S.acc)
 
     def _unit_step(self, S, k, branch):
@@ -217,7 +260,7 @@ class Pose2VideoPipeline:
         b = 0 if branch == "uncond" else 1
         x = ops.gather_window(S.lat, idx, 1, 64)
         pred = self.denoising_unet.forward_nhwc(x, 1, idx.numel(), S.t_dev, S.ehs[b:b + 1], S.win_pose[k],
-                                                ref_branch=branch)
+                                                ref_branch=branch, ehs_key=S.video_key)
         ops.scatter_accumulate(pred, idx, S.acc[b:b + 1])
 
     def _reset_block_caches(self):
@@ -233,10 +276,16 @@ class Pose2VideoPipeline:
     def _weights_fingerprint(self):
         return hash(tuple((p.data_ptr(), p._version) for m in self._nn_modules() for p in m.parameters()))
 
-    def _new_session(self, clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, static):
+    def _new_session(self, clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, units, static,
+                     shard):
         device = self.device
         S = _Session()
-        S.clip_is_embed, S.dup, S.static = clip_is_embed, dup, static
+        # key of the per-block step-invariant caches (attn2 constant, bank K/V): one per session, never reused, so a later
+        # video can not hit an earlier video's constants (a static session keeps its key: its graphs rewrite the same
+        # buffers for every video)
+        Pose2VideoPipeline._video_counter += 1
+        S.video_key = ("video", id(self), Pose2VideoPipeline._video_counter)
+        S.clip_is_embed, S.dup, S.static, S.shard, S.units = clip_is_embed, dup, static, shard, list(units)
         enc_dtype = self.image_encoder.dtype if isinstance(self.image_encoder, torch.nn.Module) else torch.float16
 
         def own(t, dtype):   # static sessions own their input buffers (graphs read them on every replay)
@@ -257,39 +306,67 @@ class Pose2VideoPipeline:
                                              batch_size=1, fusion_blocks="full")
         S.reader = ReferenceAttentionControl(self.denoising_unet, do_classifier_free_guidance=cfg, mode="read",
                                              batch_size=1, fusion_blocks="full")
-        S.g_embed = S.g_reference = None
-        S.g_windows = []
-        S.n_embed = S.n_reference = 0
-        S.n_windows = []
+        S.g_embed = S.g_reference = S.g_write = None
+        S.g_units = []
+        S.n_embed = S.n_reference = S.n_write = 0
+        S.n_units = []
+        S.bank_shapes = S.bank_flat = None
         return S
 
     def _capture(self, fn, pool=None):
-        """Capture fn() on the side stream; returns (graph, number of this library's kernels recorded in it)."""
+        """Capture fn() on the side stream; returns (graph, number of this library's kernels recorded in it).
+        thread_local capture mode: a process group's watchdog thread may touch the CUDA runtime while we capture."""
         g = torch.cuda.CUDAGraph()
         n0 = ops.KERNEL_LAUNCHES
-        with torch.cuda.graph(g, pool=pool, stream=self._side_stream):
+        with torch.cuda.graph(g, pool=pool, stream=self._side_stream, capture_error_mode="thread_local"):
             fn()
         n = ops.KERNEL_LAUNCHES - n0
         ops.KERNEL_LAUNCHES = n0     # recorded, not launched: replays are what count
         return g, n
 
+    def _exchange_banks(self, S, first: bool):
+        """Sharded sessions: ONE NCCL broadcast of the flat bank buffer (rank 0 -> all) per video; on the first video of a
+        session also the shape handshake and the buffer allocation. All ranks end with the writer banks as views of it."""
+        if first:
+            S.bank_shapes = self._bank_layout(S)
+            S.bank_flat = torch.empty(sum(a * b * c for a, b, c in S.bank_shapes), dtype=torch.float16, device=S.lat.device)
+            if torch.distributed.get_rank() == 0:
+                self._pack_banks(S)
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        torch.distributed.broadcast(S.bank_flat, 0)
+        ev1.record()
+        self._comm_events.append(("bank_broadcast_ms", ev0, ev1))
+        self._unpack_banks(S)
+
     def _build_static_session(self, S, mark):
         """First video of a geometry: one eager pass (lazy initialisation: cuDNN plans, kernel attributes, weight packing),
-        then every stage is captured. Later videos only copy their inputs into S and replay."""
+        then every stage is captured. Later videos only copy their inputs into S and replay.
+        Sharded sessions (S.shard): rank 0 alone runs the ReferenceNet write pass (+ packs the banks into the flat buffer);
+        the bank broadcast stays an eager NCCL call between the write graph and the read graph."""
         device = self.device
+        rank0 = (not S.shard) or torch.distributed.get_rank() == 0
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=device)
         side = self._side_stream
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             self._stage_embed(S)
-            self._stage_reference_write(S)
+            if rank0:
+                self._stage_reference_write(S)
+        torch.cuda.current_stream(device).wait_stream(side)
+        if S.shard:
+            self._exchange_banks(S, first=True)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
             self._stage_reference_read(S)
-            if S.win_idx:
-                self._window_step(S, 0)
+            if S.units:
+                self._unit_step(S, *S.units[0])
             S.acc.zero_()
             S.reader.clear()
-            S.writer.clear()
+            if not S.shard:
+                S.writer.clear()
         torch.cuda.current_stream(device).wait_stream(side)
         mark("warm_pass_ms")
         self._reset_block_caches()
@@ -301,17 +378,43 @@ class Pose2VideoPipeline:
                 warnings.warn(f"CLIP / VAE-encode stage not graph-capturable ({type(e).__name__}: {e}); running it eagerly")
                 S.g_embed = None
                 torch.cuda.synchronize(device)
+        if S.shard:
+            if rank0:
+                def write():
+                    S.writer.clear()
+                    self._stage_reference_write(S)
+                    self._pack_banks(S)
+                S.g_write, S.n_write = self._capture(write)
+            self._unpack_banks(S)
 
-        def reference():
-            self._stage_reference_write(S)
-            self._stage_reference_read(S)
-        S.g_reference, S.n_reference = self._capture(reference)
+            def read():
+                self._stage_reference_read(S)
+            S.g_reference, S.n_reference = self._capture(read, pool=S.g_write.pool() if S.g_write is not None else None)
+        else:
+            def reference():
+                self._stage_reference_write(S)
+                self._stage_reference_read(S)
+            S.g_reference, S.n_reference = self._capture(reference)
         pool = S.g_reference.pool()
-        for k in range(len(S.win_idx)):
-            g, n = self._capture(lambda k=k: self._window_step(S, k), pool=pool)
-            S.g_windows.append(g)
-            S.n_windows.append(n)
+        for k, branch in S.units:
+            g, n = self._capture(lambda k=k, branch=branch: self._unit_step(S, k, branch), pool=pool)
+            S.g_units.append(g)
+            S.n_units.append(n)
         mark("graph_capture_ms")
+
+    def _replay_prologue(self, S):
+        if S.g_embed is not None:
+            S.g_embed.replay()
+            ops._count(S.n_embed)
+        else:
+            self._stage_embed(S)
+        if S.shard:
+            if S.g_write is not None:
+                S.g_write.replay()
+                ops._count(S.n_write)
+            self._exchange_banks(S, first=False)
+        S.g_reference.replay()
+        ops._count(S.n_reference)
 
     # -------------------------------------------------------------------------------------------- device core
     @torch.no_grad()
@@ -323,12 +426,14 @@ class Pose2VideoPipeline:
         pose_cond [L,3,H,W] (pose maps as the reference's cond_image_processor emits them); latents [1,4,L,h,w].
         Returns the decoded video on the device, fp16 [1,3,L,H,W] in [0,1] (None if decode=False).
 
-        Single GPU and dist_mode="clips": all stages of a video geometry are captured into CUDA graphs once (a cached
-        _Session) and replayed for every later video. dist_mode="windows" runs eagerly (NCCL bank broadcast + per-step
-        all-reduce between the stages); its per-window UNet call is GPU-bound even when launched from Python."""
+        All stages of a video geometry are captured into CUDA graphs once (a cached _Session) and replayed for every later
+        video — also in the sharded modes ("windows" / "window_branches"), where each rank captures ITS units and the two
+        collectives stay eager NCCL calls between graph replays: one broadcast of the flat bank buffer per video, one fp32
+        all-reduce of the prediction accumulator per DDIM step. use_cuda_graph=False runs the same stages eagerly."""
         device = self.device
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
+        self._comm_events = []
         detail = {} if getattr(self, "profile_phases", False) else None
         t_mark = [time.perf_counter()]
 
@@ -341,6 +446,7 @@ class Pose2VideoPipeline:
         self.phase_detail = detail
         cfg = guidance_scale > 1.0
         dup = 2 if cfg else 1
+        pred_type, clip_range = self._scheduler_update_rule()
         self.scheduler.set_timesteps(num_inference_steps, device=device)
         timesteps = [int(t) for t in self.scheduler.timesteps]
         rank, world = 0, 1
@@ -364,16 +470,18 @@ class Pose2VideoPipeline:
         inv_count = inv_count.to(device=device, dtype=torch.float32)
         clip_is_embed = clip_image_embeds is not None
         clip_in = clip_image_embeds if clip_is_embed else clip_pixels
-        static = bool(self.use_cuda_graph) and not shard
+        static = bool(self.use_cuda_graph)
 
         if static:
-            key = (L, h, w, dup, tuple(tuple(wd) for wd in my_windows), clip_is_embed, tuple(clip_in.shape),
-                   tuple(ref_image_tensor.shape), tuple(pose_cond.shape), self._weights_fingerprint())
+            key = (L, h, w, dup, tuple(tuple(wd) for wd in my_windows), tuple(units), shard, rank, world, clip_is_embed,
+                   tuple(clip_in.shape), tuple(ref_image_tensor.shape), tuple(pose_cond.shape),
+                   self._weights_fingerprint())
             S = self._sessions.get(key)
             if S is None:
                 while len(self._sessions) >= self.max_sessions:     # each session pins ~10 GB of activations
                     self._sessions.pop(next(iter(self._sessions)))
-                S = self._new_session(clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, True)
+                S = self._new_session(clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, units,
+                                      True, shard)
                 S.lat.copy_(latents[0].permute(1, 2, 3, 0))
                 self._build_static_session(S, mark)
                 self._sessions[key] = S
@@ -383,23 +491,18 @@ class Pose2VideoPipeline:
                 S.pose_cond.copy_(pose_cond)
                 S.lat.copy_(latents[0].permute(1, 2, 3, 0))
                 S.acc.zero_()
-            if S.g_embed is not None:
-                S.g_embed.replay()
-                ops._count(S.n_embed)
-            else:
-                self._stage_embed(S)
-            S.g_reference.replay()
-            ops._count(S.n_reference)
+            self._replay_prologue(S)
             mark("prologue_replay_ms")
         else:
-            S = self._new_session(clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, False)
+            S = self._new_session(clip_in, clip_is_embed, ref_image_tensor, pose_cond, L, h, w, dup, my_windows, units,
+                                  False, shard)
             S.lat.copy_(latents[0].permute(1, 2, 3, 0))
             self._stage_embed(S)
             mark("embed_ms")
-            if world == 1 or rank == 0 or not shard:
+            if not shard or rank == 0:
                 self._stage_reference_write(S)
             if shard:
-                self._broadcast_banks(S.writer, device)
+                self._exchange_banks(S, first=True)
             self._stage_reference_read(S)
             mark("reference_ms")
         lat, acc = S.lat, S.acc
@@ -410,16 +513,20 @@ class Pose2VideoPipeline:
             for i, t in enumerate(timesteps):
                 S.t_dev.fill_(float(t))
                 if static:
-                    for g, n in zip(S.g_windows, S.n_windows):
+                    for g, n in zip(S.g_units, S.n_units):
                         g.replay()
                         ops._count(n)
                 else:
                     for k, branch in units:
                         self._unit_step(S, k, branch)
                 if shard:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                     torch.distributed.all_reduce(acc)
+                    e1.record()
+                    self._comm_events.append(("all_reduce_ms", e0, e1))
                 a_t, a_p = self._alpha_pair(t)
-                ops.cfg_ddim_step(acc, inv_count, float(guidance_scale), a_t, a_p, lat)
+                ops.cfg_ddim_step(acc, inv_count, float(guidance_scale), a_t, a_p, lat, pred_type, clip_range)
                 progress_bar.update()
                 if callback is not None and i % callback_steps == 0:
                     callback(i, t, lat.permute(3, 0, 1, 2).unsqueeze(0))
@@ -437,8 +544,12 @@ class Pose2VideoPipeline:
         if decode:
             if shard and L % world == 0:   # frames sharded over ranks, gathered on every rank
                 part = self.decode_latents_device(latents_out[:, :, rank::world]).contiguous()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
                 parts = [torch.empty_like(part) for _ in range(world)]
                 torch.distributed.all_gather(parts, part)
+                e1.record()
+                self._comm_events.append(("all_gather_ms", e0, e1))
                 video = torch.empty(1, 3, L, part.shape[-2], part.shape[-1], device=device, dtype=part.dtype)
                 for r in range(world):
                     video[:, :, r::world] = parts[r]
@@ -446,7 +557,7 @@ class Pose2VideoPipeline:
                 video = self.decode_latents_device(latents_out)
         ev[3].record()
         self._events = ev
-        self._meta = dict(windows=len(windows), steps=len(timesteps))
+        self._meta = dict(windows=len(windows), steps=len(timesteps), units_this_rank=len(units))
         return video
 
     def clear_graph_cache(self):
@@ -458,6 +569,10 @@ class Pose2VideoPipeline:
         ev = self._events
         self.timings = dict(reference_ms=ev[0].elapsed_time(ev[1]), denoise_ms=ev[1].elapsed_time(ev[2]),
                             decode_ms=ev[2].elapsed_time(ev[3]), **self._meta)
+        # collectives of the sharded modes: device time between the records around each NCCL call (includes waiting for
+        # the slowest rank: a rank that finished its units early sits in the all-reduce)
+        for name, e0, e1 in getattr(self, "_comm_events", []):
+            self.timings[name] = self.timings.get(name, 0.0) + e0.elapsed_time(e1)
         return self.timings
 
     # -------------------------------------------------------------------------------------------- __call__

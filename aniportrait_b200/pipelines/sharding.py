@@ -20,7 +20,7 @@ def plan_windows(num_frames: int, num_inference_steps: int, context_schedule="un
                                                            context_stride, context_overlap))
     counts = torch.zeros(num_frames)
     for wd in windows:
-        for f in wd:
+        for f in set(wd):     # a frame repeated inside one window counts once (reference :546-548: counter[:, :, c] += 1)
             counts[f] += 1
     if (counts == 0).any():
         raise ValueError("context schedule leaves frames uncovered")
@@ -64,7 +64,8 @@ def plan_units(n_windows: int, cfg: bool, world: int, cond_cost: float = 1.2) ->
 
 def accumulate(acc: torch.Tensor, pred: torch.Tensor, window: List[int]):
     """CPU reference of ap_scatter_accumulate_f16: acc[b, window[f]] += pred[b, f] (acc fp32 [B, L, ...])."""
-    for j, f in enumerate(window):
+    last = {f: j for j, f in enumerate(window)}     # repeated frame: its last occurrence wins, counted once
+    for f, j in last.items():
         acc[:, f] += pred[:, j].to(acc.dtype)
     return acc
 

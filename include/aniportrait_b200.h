@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AP_VERSION 100
+#define AP_VERSION 200
 
 #define AP_OK 0
 #define AP_ERR_INVALID (-1)  /* bad argument / unsupported shape */
@@ -121,14 +121,20 @@ int ap_nhwc_to_ncfhw_f16(const void* x, void* out, int B, int C, int F, int HW, 
 
 /*
  * Denoising-loop elementwise ops (reference src/pipelines/pipeline_pose2vid_long.py:521-559 and diffusers
- * DDIMScheduler.step, v-prediction, eta = 0). latents: fp16 [L, HW, 4] channels-last; acc: fp32 [B, L, HW, 4].
+ * DDIMScheduler.step [dep], eta = 0). latents: fp16 [L, HW, 4] channels-last; acc: fp32 [B, L, HW, 4].
+ * ap_cfg_ddim_step_f16: overlap average + classifier-free guidance + one DDIM update, in place on `latents`; `acc` is
+ * zeroed. prediction_type: AP_PRED_* (configs/inference/inference_v2.yaml:30 uses v_prediction, inference_v1.yaml
+ * epsilon); clip_range > 0 clamps the predicted x0 to [-clip_range, clip_range] (DDIMScheduler clip_sample), <= 0: off.
  */
+#define AP_PRED_V 0
+#define AP_PRED_EPSILON 1
+#define AP_PRED_SAMPLE 2
 int ap_gather_window_f16(const void* latents, const int* frame_idx, void* out, int dup, int F, int HW, int Cpad,
                          void* stream);
 int ap_scatter_accumulate_f16(const void* pred, int ld, const int* frame_idx, float* acc, int B, int F, int L, int HW,
                               void* stream);
 int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg, float guidance, float alpha_t, float alpha_prev,
-                         void* latents, int L, int HW, void* stream);
+                         int prediction_type, float clip_range, void* latents, int L, int HW, void* stream);
 
 #ifdef __cplusplus
 }

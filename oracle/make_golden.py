@@ -140,8 +140,87 @@ def case_pipeline(name="pipeline_small", P=PIPE_SMALL):
           f"in {time.time() - t0:.1f}s")
 
 
+PIPE_C1_FULL = dict(chans=(320, 640, 1280, 1280), vae_chans=(128, 256, 512, 512), size=512, L=4, steps=10,
+                    guidance=3.5, clip="vit_l_14",
+                    seeds=dict(unet3d=401, unet2d=402, pose=403, vae=404, clip=405, inputs=406, latents=42))
+
+
+def full_clip_encoder(seed):
+    """CLIP ViT-L/14 vision tower (the architecture of sd-image-variations' image_encoder), seeded random weights."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cfg = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                           image_size=224, patch_size=14, projection_dim=768)
+    torch.manual_seed(seed)
+    m = CLIPVisionModelWithProjection(cfg)
+    m.load_state_dict(randomize_state_dict(m.state_dict(), seed=seed))
+    return m.eval()
+
+
+class _PhaseTimer:
+    """Wall seconds spent inside the forward of each top-level module of the reference pipeline (hooks only: the
+    reference code itself is not touched)."""
+
+    def __init__(self, **modules):
+        self.seconds = {k: 0.0 for k in modules}
+        self.calls = {k: 0 for k in modules}
+        self._t = {}
+        for name, m in modules.items():
+            m.register_forward_pre_hook(lambda mod, inp, name=name: self._t.__setitem__(name, time.perf_counter()))
+            m.register_forward_hook(lambda mod, inp, out, name=name: self._done(name))
+
+    def _done(self, name):
+        self.seconds[name] += time.perf_counter() - self._t[name]
+        self.calls[name] += 1
+
+
+def case_pipeline_c1(name="pipeline_c1_full", P=PIPE_C1_FULL):
+    """BASELINE.json configs[0]: the UNMODIFIED reference Pose2VideoPipeline at the real model sizes,
+    512x512, L=4, 10 DDIM steps, CFG 3.5, fp32 on the host cores. Besides the golden tensors the fixture records the wall
+    seconds of the run (whole call and per top-level module): the un-extrapolated CPU baseline of the reference."""
+    ref_import.activate()
+    from diffusers import AutoencoderKL, DDIMScheduler
+    from src.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline
+    t0 = time.time()
+    sd = P["seeds"]
+    unet3d = ref_import.build_unet3d(P["chans"]); _load(unet3d, sd["unet3d"])
+    unet2d = ref_import.build_unet2d(P["chans"]); _load(unet2d, sd["unet2d"])
+    pose = ref_import.build_pose_guider(P["chans"][0]); _load(pose, sd["pose"])
+    vae = AutoencoderKL(block_out_channels=P["vae_chans"]); _load(vae, sd["vae"])
+    clip = full_clip_encoder(sd["clip"])
+    pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=unet2d, denoising_unet=unet3d,
+                              pose_guider=pose, scheduler=DDIMScheduler(**SCHED_KWARGS))
+    t_build = time.time() - t0
+    ref_image, poses, ref_pose = pipeline_inputs(P["size"], P["L"], sd["inputs"])
+    timer = _PhaseTimer(denoising_unet=unet3d, reference_unet=unet2d, pose_guider=pose, image_encoder=clip,
+                        vae_decoder=vae.decoder, vae_encoder=vae.encoder)
+    lat_trace = []
+    t1 = time.perf_counter()
+    out = pipe(ref_image, poses, ref_pose, P["size"], P["size"], P["L"], P["steps"], P["guidance"],
+               generator=torch.manual_seed(sd["latents"]), callback=lambda i, t, l: lat_trace.append(l.clone()),
+               callback_steps=1)
+    wall = time.perf_counter() - t1
+    videos = out.videos
+    torch.save(dict(case=name, params={k: v for k, v in P.items()}, final_latents=lat_trace[-1].float(),
+                    first_step_latents=lat_trace[0].float(), video_frames=videos[:, :, [0, P["L"] - 1]].half(),
+                    video_frame_means=videos.mean(dim=(0, 1, 3, 4)).float(), torch_version=str(torch.__version__),
+                    cpu_reference=dict(wall_s=wall, frames=P["L"], frames_per_s=P["L"] / wall,
+                                       threads=torch.get_num_threads(), nproc=os.cpu_count(),
+                                       phase_seconds=dict(timer.seconds), phase_calls=dict(timer.calls),
+                                       build_s=t_build, dtype="fp32",
+                                       how="time.perf_counter() around the unmodified reference "
+                                           "Pose2VideoPipeline.__call__ (oracle/diffusers_shim leaves), one run, no warm-up"),
+                    generator="reference Pose2VideoPipeline via oracle/diffusers_shim, fp32 CPU"),
+               os.path.join(GOLDEN, name + ".pt"))
+    print(f"{name}: videos {tuple(videos.shape)} mean={videos.mean():.4f} steps traced={len(lat_trace)} wall={wall:.1f}s "
+          f"phases={ {k: round(v, 1) for k, v in timer.seconds.items()} } total {time.time() - t0:.1f}s")
+
+
 CASES = {
     "pipeline_small": case_pipeline,
+    "pipeline_c1_full": case_pipeline_c1,
+    # the benchmarked geometry (BASELINE.json configs[1]): full width, 64x64 latents, one 16-frame window under CFG
+    "unet3d_full_f16_64x64": lambda: case_unet3d("unet3d_full_f16_64x64", (320, 640, 1280, 1280), 16, 64, 64, 479,
+                                                  seeds=(121, 122, 123)),
     # full SD1.5 width (the real model size), 256x256-pixel equivalent latents, 4-frame window
     "unet3d_full_f4_32x32": lambda: case_unet3d("unet3d_full_f4_32x32", (320, 640, 1280, 1280), 4, 32, 32, 479),
     # reduced width, 16-frame window (temporal attention at the production window length), non-square latent

@@ -17,4 +17,9 @@ def cuda_dev():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # fp32 torch evaluations on the device are test ORACLES: keep them real fp32 (torch's default lets cuDNN convolutions
+    # run in TF32, ~5e-4 relative noise, which would hide inside the kernels' tolerance)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
     return torch.device("cuda:0")

@@ -237,3 +237,82 @@ def test_short_pipelines_forward_to_the_shared_core_with_single_window_arguments
         args, kw = calls[-1]
         assert args[1] == ["pose"] and args[5] == 1 and kw["context_frames"] == 1
         assert isinstance(res, pipeline_pose2img.Pose2ImagePipelineOutput) and res.images == "RAW"
+
+
+def test_window_scheduler_degenerate_overlap_fails_like_the_reference():
+    """context_overlap == context_size * hop: the reference's range() raises ValueError (zero step); the rewritten loop must
+    not spin forever. A larger overlap (negative step) yields no window at that level in both."""
+    from aniportrait_b200.pipelines.context import uniform
+    with pytest.raises(ValueError):
+        list(uniform(0, 25, 40, 16, 1, 16))
+    assert list(uniform(0, 25, 40, 16, 1, 20)) == []
+    if os.path.isdir("/root/reference/src/pipelines"):
+        sys.path.insert(0, "/root/reference")
+        from src.pipelines.context import uniform as ref_uniform
+        with pytest.raises(ValueError):
+            list(ref_uniform(0, 25, 40, 16, 1, 16))
+        assert list(ref_uniform(0, 25, 40, 16, 1, 20)) == []
+        for args in [(0, 25, 24, 16, 2, 4), (3, 25, 50, 16, 3, 4), (0, 25, 128, 16, 1, 4)]:
+            assert list(uniform(*args)) == [list(map(int, w)) for w in ref_uniform(*args)]
+
+
+def test_repeated_frame_in_a_window_counts_once():
+    from aniportrait_b200.pipelines.sharding import accumulate, plan_windows
+    windows, inv = plan_windows(24, 25, "uniform", 16, 2, 4)
+    counts = torch.zeros(24)
+    for wd in windows:
+        for f in set(wd):
+            counts[f] += 1
+    assert torch.equal(inv, 1.0 / counts)
+    wd = next(w for w in windows if len(set(w)) < len(w))
+    acc = accumulate(torch.zeros(1, 24, 2), torch.ones(1, len(wd), 2), wd)
+    assert acc.max().item() == 1.0
+
+
+def test_checked_state_dict_loading():
+    """from_pretrained must not silently leave weights at random init: legacy VAE attention names are remapped (diffusers
+    _convert_deprecated_attention_blocks [dep]); anything missing / unknown raises unless whitelisted."""
+    from aniportrait_b200.models.modeling import load_checked
+    from aniportrait_b200.models.vae import AutoencoderKL
+    vae = AutoencoderKL(block_out_channels=(32, 32, 64, 64))
+    ren = {"to_q": "query", "to_k": "key", "to_v": "value", "to_out.0": "proj_attn"}
+
+    def legacy_name(k):
+        if ".attentions.0." in k:
+            for new, old in ren.items():
+                k = k.replace(f".{new}.", f".{old}.")
+        return k
+    legacy = {legacy_name(k): torch.randn_like(v) for k, v in vae.state_dict().items()}
+    assert any(".query." in k for k in legacy)
+    load_checked(vae, legacy)
+    for k, v in vae.state_dict().items():
+        assert torch.equal(v, legacy[legacy_name(k)])
+    broken = dict(legacy)
+    broken.pop("decoder.conv_in.weight")
+    with pytest.raises(RuntimeError, match="missing"):
+        load_checked(vae, broken)
+    extra = dict(legacy, **{"decoder.bogus.weight": torch.zeros(1)})
+    with pytest.raises(RuntimeError, match="unexpected"):
+        load_checked(vae, extra)
+    load_checked(vae, extra, allow_unexpected=("bogus",))
+
+
+def test_pipeline_rejects_schedulers_the_fused_step_cannot_reproduce():
+    from aniportrait_b200.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline
+    from aniportrait_b200.pipelines.scheduler import DDIMScheduler
+
+    class P(Pose2VideoPipeline):
+        def __init__(self, scheduler):
+            self.scheduler = scheduler
+    assert P(DDIMScheduler(prediction_type="v_prediction", clip_sample=False))._scheduler_update_rule() == ("v_prediction", 0.0)
+    assert P(DDIMScheduler())._scheduler_update_rule() == ("epsilon", 1.0)      # diffusers defaults: epsilon + clip_sample
+
+    class Flow:
+        config = dict(prediction_type="flow")
+    with pytest.raises(NotImplementedError):
+        P(Flow())._scheduler_update_rule()
+
+    class NoAlphas:
+        config = dict(prediction_type="epsilon")
+    with pytest.raises(NotImplementedError):
+        P(NoAlphas())._scheduler_update_rule()

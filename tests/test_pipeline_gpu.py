@@ -99,6 +99,37 @@ def test_pipeline_graph_replay_matches_eager_and_is_repeatable(cuda_dev):
     assert e_rep < 1e-6 and e_eager < 1e-6 and rel_l2(va2, va1) < 1e-6 and rel_l2(vae_, va1) < 1e-6
 
 
+def test_eager_pipe_second_video_does_not_reuse_first_videos_clip_constant(cuda_dev):
+    """the per-block attn2 constant to_out(to_v(clip)) was cached on (data_ptr, _version) of the CLIP
+    embedding; a second eager video with another reference image got the first video's conditioning. Two different CLIP
+    embeddings through ONE eager pipe (use_cuda_graph=False) must each equal the result of a fresh pipe."""
+    gold = torch.load(os.path.join(GOLDEN, "pipeline_small.pt"))
+    P = gold["params"]
+    L, steps, size = 4, 2, P["size"]
+    ref_image, poses, ref_pose = pipeline_inputs(size, L, 555)
+    lat0 = torch.randn((1, 4, L, size // 8, size // 8), generator=torch.manual_seed(11)).to(torch.float16)
+    emb_a = torch.randn(1, 768, generator=torch.manual_seed(12)).to(torch.float16)
+    emb_b = torch.randn(1, 768, generator=torch.manual_seed(13)).to(torch.float16)
+
+    def run(pipe, emb):
+        pipe(ref_image, poses, ref_pose, size, size, L, steps, P["guidance"], latents=lat0.clone(),
+             clip_image_embeds=emb.to(cuda_dev))
+        return pipe.last_latents.float().cpu()
+    shared = build_pipeline(P, cuda_dev)
+    shared.use_cuda_graph = False
+    a_shared = run(shared, emb_a)
+    b_shared = run(shared, emb_b)       # same tensor shapes: the allocator hands back the same addresses
+    fresh = build_pipeline(P, cuda_dev)
+    fresh.use_cuda_graph = False
+    b_fresh = run(fresh, emb_b)
+    assert rel_l2(a_shared, b_fresh) > 1e-3, "the two CLIP embeddings must matter"
+    assert rel_l2(b_shared, b_fresh) < 1e-6, "second video on a shared eager pipe used stale conditioning"
+    # the cached-graph path with a changed embedding (replay rewrites the constants)
+    shared.use_cuda_graph = True
+    run(shared, emb_a)
+    assert rel_l2(run(shared, emb_b), b_fresh) < 1e-6
+
+
 def _host_sd(module):
     return {k: v.detach().float().cpu() for k, v in module.state_dict().items()}
 

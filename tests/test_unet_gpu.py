@@ -33,7 +33,10 @@ def _run_product(unet3d, unet2d, sample, ehs, ref_lat, pose, timestep, dev):
     return out
 
 
-@pytest.mark.parametrize("name", ["unet3d_small_f16_16x24", "unet3d_full_f4_32x32"])
+# unet3d_full_f16_64x64 is the BENCHMARKED geometry (BASELINE.json configs[1]: 512x512 -> 64x64 latents, one 16-frame window
+# under CFG = 32 frames per call, full SD1.5 width): M = 131072-row GEMMs on the wide cta_group::2 tiles, 8192-key reference
+# attention (attention5_kernel) with 16 + 16 frames, temporal attention over 16 frames.
+@pytest.mark.parametrize("name", ["unet3d_small_f16_16x24", "unet3d_full_f4_32x32", "unet3d_full_f16_64x64"])
 def test_unet3d_against_reference_golden(cuda_dev, name):
     path = os.path.join(GOLDEN, name + ".pt")
     if not os.path.exists(path):
