@@ -6,18 +6,21 @@ Semantics preserved on purpose:
     so a frame's features depend on the window it is evaluated with;
   * the `ref_x` branch is dead code in the reference (its Transformer2DModel blocks are built with
     cross_attention_dim=None, pose_guider.py:86-89, so `ref_x` is never read): it is accepted and ignored.
-The four self-attention Transformer2DModel blocks (16 heads x 88) run on the sm_100a kernels; the small-channel conv /
-BatchNorm / ReLU stem (3..128 channels, 4x4 stride-2 convs, ~2.5 GFLOP/frame) currently uses fp16 torch library ops.
+Everything runs on this library's sm_100a kernels (aniportrait_b200/csrc): the 3/16/32-channel k3 / k4 convolutions of the
+stem on a direct-convolution kernel (ap_conv2d_direct_nhwc_f16), every 64..1280-channel 3x3 convolution (stride 1 and 2) on
+the tcgen05 implicit-GEMM kernel, train-mode BatchNorm + ReLU on a two-stage order-fixed reduction + apply
+(ap_batchnorm_train_nhwc_f16), the 1x1 final projection (with `scale` folded in) on the GEMM kernel, and the four
+self-attention Transformer2DModel blocks (16 heads x 88) on the GEMM / attention / norm kernels.
 It does not depend on the timestep, so the pipeline evaluates it once per window instead of once per step.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from .blocks import RunCtx, Transformer2DModel as _KernelTransformer2D
-from .modeling import ModelBase
+from .modeling import ModelBase, PackedCache, f16, f32
 
 
 class Transformer2DModel(_KernelTransformer2D):
@@ -72,15 +75,64 @@ class PoseGuider(ModelBase):
         nn.init.zeros_(self.final_proj.weight)
         nn.init.zeros_(self.final_proj.bias)
 
+    # ------------------------------------------------------------------------------------------------ packing
     @staticmethod
-    def _bn_stage(seq, x):
-        for m in seq:
-            if isinstance(m, nn.BatchNorm2d):
-                # batch statistics, biased variance; running stats are not part of the forward value
-                x = F.batch_norm(x, None, None, m.weight, m.bias, training=True, momentum=0.0, eps=m.eps)
-            else:
-                x = m(x)
-        return x
+    def _pairs(seq):
+        mods = list(seq)
+        return [(mods[i], mods[i + 1]) for i in range(0, len(mods), 3)]     # (Conv2d, BatchNorm2d), ReLU follows
+
+    def packed(self):
+        if not hasattr(self, "_pk"):
+            self._pk = PackedCache()
+
+        def pad8(v, n, fill=0.0):
+            out = torch.full((n,), fill, dtype=torch.float32, device=v.device)
+            out[:v.numel()] = f32(v)
+            return out
+
+        def build():
+            def layer(conv, bn, cin_have):
+                """cin_have: channel count of the incoming channels-last buffer (>= conv.in_channels, zero padded)."""
+                cin, cout, k, st = conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0]
+                if cin < 64:      # small-channel direct convolution; channels padded to multiples of 8 / 16
+                    cout_p = 8 if cout <= 8 else (cout + 15) // 16 * 16
+                    d = dict(kind="direct", w=ops.pack_conv_direct_weight(conv.weight.detach(), cin_have, cout_p),
+                             b=pad8(conv.bias, cout_p), stride=st, cout=cout_p)
+                else:             # tcgen05 implicit-GEMM 3x3
+                    assert k == 3 and cin == cin_have
+                    w = ops.pack_conv3x3_weight(conv.weight.detach())
+                    cout_p = cout
+                    d = dict(kind="igemm", w=w, b=pad8(conv.bias, w.shape[0]), stride=st, cout=cout)
+                # padded channels: gamma = beta = 0 keeps them exactly zero through BatchNorm + ReLU
+                d.update(g=pad8(bn.weight, cout_p), be=pad8(bn.bias, cout_p), eps=bn.eps)
+                return d, cout_p
+            stem, c = [], 8      # the pose map arrives as [frames, H, W, 8] (3 channels zero padded)
+            for conv, bn in self._pairs(self.conv_layers):
+                d, c = layer(conv, bn, c)
+                stem.append(d)
+            cfin = self.final_proj.out_channels
+            sc = self.scale.detach().to(torch.float32)
+            pk = dict(stem=stem,
+                      # (W x + b) * scale == (scale W) x + scale b  (reference pose_guider.py:129-131)
+                      wf=f16(self.final_proj.weight.detach().to(torch.float32).reshape(cfin, -1) * sc),
+                      bf=(f32(self.final_proj.bias) * sc).contiguous(), stages=[])
+            c = cfin
+            for k in range(1, 5):
+                st = []
+                for conv, bn in self._pairs(getattr(self, f"conv_layers_{k}")):
+                    d, c = layer(conv, bn, c)
+                    st.append(d)
+                pk["stages"].append(st)
+            return pk
+        return self._pk.get(self, build)
+
+    @staticmethod
+    def _conv_bn_relu(x, d):
+        if d["kind"] == "direct":
+            y = ops.conv2d_direct(x, d["w"], d["stride"], 1, bias=d["b"])
+        else:
+            y = ops.conv3x3(x, d["w"], d["cout"], bias=d["b"], stride=d["stride"])
+        return ops.batch_norm_train(y, d["g"], d["be"], d["eps"], relu=True)
 
     @torch.no_grad()
     def forward_nhwc(self, x: torch.Tensor):
@@ -88,15 +140,20 @@ class PoseGuider(ModelBase):
         the batch leaves BatchNorm's batch statistics unchanged)."""
         if not x.is_cuda:
             raise RuntimeError("aniportrait_b200.PoseGuider runs on CUDA only: no CPU fallback")
-        ctx = RunCtx(1, x.shape[0], None, None)
-        fea = []
-        x = self._bn_stage(self.conv_layers, x)
-        x = self.final_proj(x) * self.scale
-        x = x.permute(0, 2, 3, 1).contiguous()
-        fea.append(x)
+        if self.dtype != torch.float16:
+            raise RuntimeError("aniportrait_b200.PoseGuider runs in fp16 (`.to(device, torch.float16)`): no fp32 / library path")
+        pk = self.packed()
+        frames, cin, H, W = x.shape
+        ctx = RunCtx(1, frames, None, None)
+        x = ops.ncfhw_to_nhwc(x.to(torch.float16).contiguous().view(frames, cin, 1, H, W), 8)      # [frames, H, W, 8]
+        for d in pk["stem"]:
+            x = self._conv_bn_relu(x, d)
+        nf, h, w, c = x.shape
+        x = ops.gemm(x.view(-1, c), pk["wf"], bias=pk["bf"]).view(nf, h, w, -1)
+        fea = [x]
         for k in range(1, 5):
-            xc = self._bn_stage(getattr(self, f"conv_layers_{k}"), x.permute(0, 3, 1, 2))
-            x = xc.permute(0, 2, 3, 1).contiguous()
+            for d in pk["stages"][k - 1]:
+                x = self._conv_bn_relu(x, d)
             if self.use_ca:
                 x = getattr(self, f"cross_attn{k}").run(x, ctx)
             fea.append(x)

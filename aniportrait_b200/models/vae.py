@@ -2,18 +2,20 @@
 
 Role on the hot path: `decode` of the denoised latents (reference pipeline_pose2vid_long.py:113-126, one frame per
 call) and a single `encode` of the reference image (once per video, :430-431).
-  * `decode` on a CUDA fp16 model runs on the sm_100a kernels (channels-last, batched over frames): implicit-GEMM 3x3
-    convs, fused GroupNorm+SiLU, tcgen05 GEMMs for the 1x1 shortcuts and the mid-block attention, which (single head,
-    d = 512: too wide for the fused attention kernel's TMEM budget) is evaluated per frame as GEMM -> row-softmax -> GEMM.
-  * `encode` on a CUDA fp16 model takes the same kernels (the stride-2 downsamplers as stride-1 convolutions whose odd
-    outputs are gathered); any non-fp16 / non-CUDA use runs as torch library ops.
+  * `decode` runs on the sm_100a kernels (channels-last, batched over frames): implicit-GEMM 3x3 convs, fused
+    GroupNorm+SiLU, tcgen05 GEMMs for the 1x1 shortcuts, the 4x4 / 8x8 (post_)quant 1x1 convs and the mid-block attention,
+    which (single head, d = 512: too wide for the fused attention kernel's TMEM budget) is evaluated per frame as
+    GEMM -> row-softmax -> GEMM.
+  * `encode` takes the same kernels (the stride-2 downsamplers as stride-1 convolutions whose odd outputs are gathered).
+There is no torch-op / CPU / fp32 path: the modules below are parameter holders (state-dict surface) with a kernel `run`;
+calling encode / decode on anything but a CUDA fp16 model with 64-multiple block widths raises. (The fp32 torch evaluation
+used by the tests lives in oracle/functional.py: vae_decode / vae_encode.)
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
@@ -30,11 +32,6 @@ class _Resnet(nn.Module):
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
-    def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
-        return (self.conv_shortcut(x) if self.conv_shortcut is not None else x) + h
-
 
 class _Attn(nn.Module):
     def __init__(self, c, groups=32, eps=1e-6):
@@ -43,13 +40,6 @@ class _Attn(nn.Module):
         self.to_q, self.to_k, self.to_v = nn.Linear(c, c), nn.Linear(c, c), nn.Linear(c, c)
         self.to_out = nn.ModuleList([nn.Linear(c, c), nn.Dropout(0.0)])
 
-    def forward(self, x):
-        b, c, h, w = x.shape
-        t = self.group_norm(x).view(b, c, h * w).transpose(1, 2)
-        q, k, v = self.to_q(t)[:, None], self.to_k(t)[:, None], self.to_v(t)[:, None]
-        a = F.scaled_dot_product_attention(q, k, v)[:, 0]
-        return x + self.to_out[0](a).transpose(1, 2).reshape(b, c, h, w)
-
 
 class _Mid(nn.Module):
     def __init__(self, c, groups):
@@ -57,20 +47,12 @@ class _Mid(nn.Module):
         self.attentions = nn.ModuleList([_Attn(c, groups)])
         self.resnets = nn.ModuleList([_Resnet(c, c, groups), _Resnet(c, c, groups)])
 
-    def forward(self, x):
-        return self.resnets[1](self.attentions[0](self.resnets[0](x)))
-
 
 class _Sampler(nn.Module):
     def __init__(self, c, down):
         super().__init__()
         self.down = down
         self.conv = nn.Conv2d(c, c, 3, stride=2 if down else 1, padding=0 if down else 1)
-
-    def forward(self, x):
-        if self.down:
-            return self.conv(F.pad(x, (0, 1, 0, 1)))
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
 
 
 class _Stage(nn.Module):
@@ -82,15 +64,6 @@ class _Stage(nn.Module):
         elif sampler == "up":
             self.upsamplers = nn.ModuleList([_Sampler(cout, False)])
         self._sampler = sampler
-
-    def forward(self, x):
-        for r in self.resnets:
-            x = r(x)
-        if self._sampler == "down":
-            x = self.downsamplers[0](x)
-        elif self._sampler == "up":
-            x = self.upsamplers[0](x)
-        return x
 
 
 # ------------------------------------------------------------------------------------------------ kernel-path helpers
@@ -162,33 +135,40 @@ class Encoder(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(boc[-1], 2 * latent, 3, padding=1)
 
-    def forward(self, x):
-        x = self.conv_in(x)
-        for b in self.down_blocks:
-            x = b(x)
-        return self.conv_out(F.silu(self.conv_norm_out(self.mid_block(x))))
-
     # ------------------------------------------------------------------------------------------ kernel path
-    def _packed(self):
+    def _packed(self, quant_conv: nn.Conv2d):
         if not hasattr(self, "_pk"):
             self._pk = PackedCache()
+            self._pk_quant = None
 
         def build():
+            # quant_conv (1x1, 8 -> 8) directly follows conv_out (3x3): their composition is ONE 3x3 convolution with
+            # W'[o, c, ky, kx] = sum_k Wq[o, k] W_out[k, c, ky, kx],  b' = Wq b_out + bq   (exact; folded in fp32)
+            wq = quant_conv.weight.detach().to(torch.float32).reshape(quant_conv.out_channels, -1)
+            w_out = torch.einsum("ok,kcyx->ocyx", wq, self.conv_out.weight.detach().to(torch.float32))
+            b_out = wq @ self.conv_out.bias.detach().to(torch.float32) + quant_conv.bias.detach().to(torch.float32)
+            wo = ops.pack_conv3x3_weight(w_out)
+            bo = torch.zeros(wo.shape[0], dtype=torch.float32, device=wo.device)
+            bo[:b_out.numel()] = b_out
             return dict(conv_in=_pack_conv(self.conv_in),
                         down=[dict(res=[_pack_res(r) for r in b.resnets],
                                    down=_pack_conv(b.downsamplers[0].conv) if b._sampler == "down" else None)
                               for b in self.down_blocks],
                         mid=[_pack_res(r) for r in self.mid_block.resnets], attn=_pack_attn(self.mid_block.attentions[0]),
-                        gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)), conv_out=_pack_conv(self.conv_out))
+                        gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)), conv_out=(wo, bo))
+        qkey = tuple((p.data_ptr(), p._version) for p in quant_conv.parameters())
+        if qkey != self._pk_quant:      # the cache below is keyed on this module's parameters only
+            self._pk._key = None
+            self._pk_quant = qkey
         return self._pk.get(self, build)
 
-    def run_nhwc(self, x: torch.Tensor, groups: int = 32) -> torch.Tensor:
-        """x: [Nf, H, W, 64] fp16 (3 image channels zero padded) -> moments [Nf, H/8, W/8, 2*latent] fp16.
+    def run_nhwc(self, x: torch.Tensor, quant_conv: nn.Conv2d, groups: int = 32) -> torch.Tensor:
+        """x: [Nf, H, W, 64] fp16 (3 image channels zero padded) -> moments AFTER quant_conv [Nf, H/8, W/8, 2*latent] fp16.
         diffusers' Downsample2D pads right/bottom by one and convolves with stride 2 and no padding:
         out[o] = sum_k w[k] x[2o + k]. That is every other output of the ordinary stride-1, pad-1 convolution
         (y[p] = sum_k w[k] x[p + k - 1], p = 2o + 1), which the implicit-GEMM kernel computes; the odd rows / columns are
         then gathered (4x the FLOPs of three small layers instead of a dedicated asymmetric-padding mode)."""
-        pk = self._packed()
+        pk = self._packed(quant_conv)
         x = ops.conv3x3(x, pk["conv_in"][0], self.conv_in.out_channels, bias=pk["conv_in"][1])
         for blk in pk["down"]:
             for d in blk["res"]:
@@ -218,30 +198,42 @@ class Decoder(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(boc[0], cout, 3, padding=1)
 
-    def forward(self, z):
-        x = self.mid_block(self.conv_in(z))
-        for b in self.up_blocks:
-            x = b(x)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
-
     # ------------------------------------------------------------------------------------------ kernel path
-    def _packed(self):
+    def _packed(self, post_quant_conv: nn.Conv2d):
         if not hasattr(self, "_pk"):
             self._pk = PackedCache()
+            self._pk_quant = None
 
         def build():
-            return dict(conv_in=_pack_conv(self.conv_in), mid=[_pack_res(r) for r in self.mid_block.resnets],
+            # post_quant_conv (1x1, 4 -> 4) precedes conv_in (3x3, zero padding): folded into conv_in over the input
+            # [z (4 channels), 1 (a constant-one channel)]: W'[o, c<4] = sum_k W_in[o, k] Wq[k, c], W'[o, 4] = sum_k W_in[o, k]
+            # bq[k]. The ones channel is zero outside the image like every padded tap, so the bias term vanishes at the
+            # border exactly as in conv_in(post_quant_conv(z)).
+            lat = post_quant_conv.in_channels
+            wq = post_quant_conv.weight.detach().to(torch.float32).reshape(post_quant_conv.out_channels, lat)
+            w_in = self.conv_in.weight.detach().to(torch.float32)                       # [C, 4, 3, 3]
+            w_fold = torch.zeros(w_in.shape[0], lat + 1, 3, 3, dtype=torch.float32, device=w_in.device)
+            w_fold[:, :lat] = torch.einsum("okyx,kc->ocyx", w_in, wq)
+            w_fold[:, lat] = torch.einsum("okyx,k->oyx", w_in, post_quant_conv.bias.detach().to(torch.float32))
+            wi = ops.pack_conv3x3_weight(w_fold)
+            bi = torch.zeros(wi.shape[0], dtype=torch.float32, device=wi.device)
+            bi[:self.conv_in.out_channels] = f32(self.conv_in.bias)
+            return dict(conv_in=(wi, bi), mid=[_pack_res(r) for r in self.mid_block.resnets],
                         attn=_pack_attn(self.mid_block.attentions[0]),
                         up=[dict(res=[_pack_res(r) for r in b.resnets],
                                  up=_pack_conv(b.upsamplers[0].conv) if b._sampler == "up" else None)
                             for b in self.up_blocks],
                         gn=(f32(self.conv_norm_out.weight), f32(self.conv_norm_out.bias)),
                         conv_out=_pack_conv(self.conv_out))
+        qkey = tuple((p.data_ptr(), p._version) for p in post_quant_conv.parameters())
+        if qkey != self._pk_quant:
+            self._pk._key = None
+            self._pk_quant = qkey
         return self._pk.get(self, build)
 
-    def run_nhwc(self, z: torch.Tensor, groups: int = 32) -> torch.Tensor:
-        """z: [Nf, h, w, 64] fp16 (4 latent channels zero padded) -> [Nf, 8h, 8w, 3] fp16."""
-        pk = self._packed()
+    def run_nhwc(self, z: torch.Tensor, post_quant_conv: nn.Conv2d, groups: int = 32) -> torch.Tensor:
+        """z: [Nf, h, w, 64] fp16 (channels: 4 latent, then a constant 1, then zeros) -> [Nf, 8h, 8w, 3] fp16."""
+        pk = self._packed(post_quant_conv)
         x = ops.conv3x3(z, pk["conv_in"][0], self.conv_in.out_channels, bias=pk["conv_in"][1])
         x = _res_run(x, pk["mid"][0], groups)
         x = _mid_attn_run(x, pk["attn"], groups)
@@ -295,34 +287,37 @@ class AutoencoderKL(ModelBase):
         self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
 
+    # ------------------------------------------------------------------------------------------------ kernel path only
+    def _require_kernel_path(self, t, what):
+        boc = self.config.block_out_channels
+        if not (t.is_cuda and self.dtype == torch.float16 and all(c % 64 == 0 for c in boc)
+                and t.shape[-1] % 8 == 0 and t.shape[-2] % 8 == 0):
+            raise RuntimeError(
+                f"aniportrait_b200.AutoencoderKL.{what} runs on the sm_100a kernels only: needs a CUDA fp16 model with block "
+                f"widths that are multiples of 64 and H, W multiples of 8 (got device={t.device}, dtype={self.dtype}, "
+                f"block_out_channels={tuple(boc)}, input {tuple(t.shape)}); there is no torch-op fallback")
+
     @torch.no_grad()
     def encode(self, x, return_dict=True):
-        """x [n, 3, H, W] -> latent distribution. fp16 CUDA models with 64-multiple widths take the sm_100a kernel path
-        (set `kernel_encode = False` to force the torch modules)."""
-        if getattr(self, "kernel_encode", True) and self._kernel_decode_ok(x) and x.shape[1] <= 64 and x.shape[-1] % 64 == 0 \
-                and x.shape[-2] % 64 == 0:
-            n, c, h, w = x.shape
-            xp = torch.zeros(n, h, w, 64, dtype=torch.float16, device=x.device)
-            xp[..., :c] = x.permute(0, 2, 3, 1).to(torch.float16)
-            m = self.encoder.run_nhwc(xp, self.config.norm_num_groups).permute(0, 3, 1, 2)
-            return AutoencoderKLOutput(latent_dist=_LatentDist(self.quant_conv(m.to(self.quant_conv.weight.dtype))))
-        return AutoencoderKLOutput(latent_dist=_LatentDist(self.quant_conv(self.encoder(x))))
-
-    def _kernel_decode_ok(self, z):
-        boc = self.config.block_out_channels
-        return (z.is_cuda and self.dtype == torch.float16 and all(c % 64 == 0 for c in boc)
-                and z.shape[-1] % 8 == 0 and z.shape[-2] % 8 == 0 and (z.shape[-1] * z.shape[-2]) % 64 == 0)
+        """x [n, 3, H, W] -> latent distribution (reference pipeline_pose2vid_long.py:430-431 takes .mean)."""
+        self._require_kernel_path(x, "encode")
+        if x.shape[-1] % 64 or x.shape[-2] % 64:
+            raise RuntimeError("AutoencoderKL.encode: image height / width must be multiples of 64")
+        n, c, h, w = x.shape
+        xp = ops.ncfhw_to_nhwc(x.to(torch.float16).contiguous().view(n, c, 1, h, w), 64)        # [n, H, W, 64]
+        m = self.encoder.run_nhwc(xp, self.quant_conv, self.config.norm_num_groups)              # [n, h, w, 2*latent]
+        nl = m.shape[-1]
+        moments = ops.nhwc_to_ncfhw(m, n, nl, 1).view(n, nl, m.shape[1], m.shape[2])
+        return AutoencoderKLOutput(latent_dist=_LatentDist(moments))
 
     @torch.no_grad()
     def decode(self, z, return_dict=True, generator=None):
-        """z [n, 4, h, w] -> sample [n, 3, 8h, 8w]. fp16 CUDA models with 64-multiple widths (sd-vae-ft-mse) take the
-        sm_100a kernel path; the 4->4 post_quant 1x1 conv is a per-pixel 4x4 matmul done while converting layouts."""
-        if not self._kernel_decode_ok(z):
-            return DecoderOutput(sample=self.decoder(self.post_quant_conv(z)))
+        """z [n, 4, h, w] -> sample [n, 3, 8h, 8w] (reference pipeline_pose2vid_long.py:118-121), batched over frames."""
+        self._require_kernel_path(z, "decode")
         n, c, h, w = z.shape
-        wq = self.post_quant_conv.weight.reshape(c, c).to(torch.float32)
-        zq = torch.einsum("nchw,oc->nhwo", z.to(torch.float32), wq) + self.post_quant_conv.bias.to(torch.float32)
-        zp = torch.zeros(n, h, w, 64, dtype=torch.float16, device=z.device)
-        zp[..., :c] = zq.to(torch.float16)
-        out = self.decoder.run_nhwc(zp, self.config.norm_num_groups)
-        return DecoderOutput(sample=out.permute(0, 3, 1, 2))
+        zp = ops.ncfhw_to_nhwc(z.to(torch.float16).contiguous().view(n, c, 1, h, w), 64)         # [n, h, w, 64]
+        zp[..., c] = 1.0                                                # the constant-one channel (see Decoder._packed)
+        out = self.decoder.run_nhwc(zp, self.post_quant_conv, self.config.norm_num_groups)       # [n, 8h, 8w, 3]
+        co = out.shape[-1]
+        sample = ops.nhwc_to_ncfhw(out, n, co, 1).view(n, co, out.shape[1], out.shape[2])
+        return DecoderOutput(sample=sample)

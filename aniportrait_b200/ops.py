@@ -185,6 +185,61 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     return out
 
 
+BN_MAX_BLOCKS = 2048  # AP_BN_MAX_BLOCKS in include/aniportrait_b200.h
+_bn_ws = {}
+
+
+def batch_norm_train(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, relu: bool = True,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """nn.BatchNorm2d in TRAIN mode (batch statistics over every row of the call, biased variance) + optional ReLU.
+    x: [..., C] fp16 channels-last, C % 8 == 0; gamma/beta fp32 [C]."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    assert gamma.dtype == torch.float32 and gamma.numel() == c and beta.dtype == torch.float32 and beta.numel() == c
+    if out is None:
+        out = torch.empty_like(x)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _bn_ws.get(key)
+    if ws is None:   # sized once for the widest layer: CUDA graphs keep this pointer
+        ws = torch.empty(2 * 2048 * (BN_MAX_BLOCKS + 1), dtype=torch.float32, device=x.device)
+        _bn_ws[key] = ws
+    rc = lib().ap_batchnorm_train_nhwc_f16(ptr(x), LL(rows), I(c), fptr(gamma), fptr(beta), _lib.c_float(eps),
+                                           I(1 if relu else 0), fptr(ws), LL(ws.numel()), ptr(out), stream_ptr())
+    check(rc, "ap_batchnorm_train_nhwc_f16")
+    _count(3)
+    return out
+
+
+def pack_conv_direct_weight(w: torch.Tensor, cin_pad: int, cout_pad: int) -> torch.Tensor:
+    """[Cout, Cin, K, K] -> [cout_pad, K, K, cin_pad] fp16 (zero padded) for conv2d_direct."""
+    cout, cin, k, _ = w.shape
+    wp = torch.zeros(cout_pad, k, k, cin_pad, dtype=torch.float16, device=w.device)
+    wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1).to(torch.float16)
+    return wp.contiguous()
+
+
+def conv2d_direct(x: torch.Tensor, w_packed: torch.Tensor, stride: int, pad: int = 1,
+                  bias: torch.Tensor | None = None) -> torch.Tensor:
+    """Small-channel direct convolution. x: [Nf, H, W, Cin] fp16 (Cin in {8, 16, 32}); w_packed from
+    pack_conv_direct_weight; returns [Nf, Ho, Wo, Cout]."""
+    _ensure(x)
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 4 and w_packed.dtype == torch.float16
+    nf, h, wd, cin = x.shape
+    cout, k, _, cin_w = w_packed.shape
+    assert cin_w == cin and w_packed.is_contiguous()
+    ho, wo = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
+    out = torch.empty(nf, ho, wo, cout, dtype=torch.float16, device=x.device)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == cout
+    rc = lib().ap_conv2d_direct_nhwc_f16(ptr(x), I(cin), I(nf), I(h), I(wd), ptr(w_packed), I(cout), I(k), I(stride),
+                                         I(pad), fptr(bias), ptr(out), stream_ptr())
+    check(rc, "ap_conv2d_direct_nhwc_f16")
+    _count()
+    return out
+
+
 def softmax_rows(x: torch.Tensor) -> torch.Tensor:
     """In-place row softmax of an fp16 matrix [rows, cols] (cols even)."""
     _ensure(x)

@@ -83,6 +83,26 @@ int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf,
 int ap_layernorm_f16(const void* x, long long rows, int C, float eps, const float* gamma, const float* beta,
                      const float* pe, int rows_per_pe, int pe_period, void* out, void* stream);
 
+/*
+ * BatchNorm2d with BATCH statistics (train mode: biased variance over all `rows` = frames*H*W of the call) + optional ReLU,
+ * channels-last. Replaces nn.BatchNorm2d + nn.ReLU of the PoseGuider, which the reference never switches to eval mode
+ * (reference src/models/pose_guider.py:19-89; scripts/pose2vid.py:102-110). x/out: [rows, C] fp16, C % 8 == 0.
+ * workspace: fp32, at least 2*C*(AP_BN_MAX_BLOCKS+1) floats (per-block partial sums, then the per-channel affine pair);
+ * two-stage order-fixed reduction, double-precision finalize.
+ */
+#define AP_BN_MAX_BLOCKS 2048
+int ap_batchnorm_train_nhwc_f16(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                                int relu, float* workspace, long long workspace_floats, void* out, void* stream);
+
+/*
+ * Direct convolution for the PoseGuider stem's small channel counts (reference src/models/pose_guider.py:19-40):
+ * x [Nf, H, W, Cin] fp16 with Cin in {8 (3 padded), 16, 32}; w [Cout, K, K, Cin] fp16; (K, stride) in {(3,1), (4,2)};
+ * out [Nf, Ho, Wo, Cout], Cout % 16 == 0 (% 8 for Cin = 8, K = 3); bias fp32 [Cout] or NULL. Wider 3x3 convolutions go
+ * through ap_conv3x3_nhwc_f16.
+ */
+int ap_conv2d_direct_nhwc_f16(const void* x, int Cin, int Nf, int H, int W, const void* w, int Cout, int K, int stride,
+                              int pad, const float* bias, void* out, void* stream);
+
 /* Row softmax, fp16 in/out (may be in place), fp32 math: the VAE mid-block attention (single head, d = 512) is evaluated as
  * GEMM -> softmax -> GEMM (diffusers AutoencoderKL [dep], reference pipeline_pose2vid_long.py:118-121). */
 int ap_softmax_rows_f16(const void* x, void* out, long long rows, int cols, long long ld, void* stream);

@@ -394,3 +394,32 @@ def vae_decode(sd, z, groups=32):
             x = conv2d(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", x)
     x = F.silu(group_norm(sd, "decoder.conv_norm_out", x, groups, 1e-6))
     return conv2d(sd, "decoder.conv_out", x)
+
+
+def vae_encode(sd, x, groups=32):
+    """AutoencoderKL.encode [dep 0.24.0] -> moments (mean | logvar) as the pipeline uses it for the reference image
+    (src/pipelines/pipeline_pose2vid_long.py:430-431 takes latent_dist.mean * 0.18215). x: [n,3,H,W] -> [n,8,H/8,W/8].
+    Downsample2D(padding=0): pad right/bottom by one, 3x3 conv stride 2."""
+    def res(p, x):
+        return resnet_block(sd, p, x, None, groups, 1e-6)
+
+    x = conv2d(sd, "encoder.conv_in", x)
+    n_blocks = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder.down_blocks."))
+    for i in range(n_blocks):
+        j = 0
+        while f"encoder.down_blocks.{i}.resnets.{j}.norm1.weight" in sd:
+            x = res(f"encoder.down_blocks.{i}.resnets.{j}", x)
+            j += 1
+        if f"encoder.down_blocks.{i}.downsamplers.0.conv.weight" in sd:
+            x = conv2d(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", F.pad(x, (0, 1, 0, 1)), stride=2, padding=0)
+    x = res("encoder.mid_block.resnets.0", x)
+    p = "encoder.mid_block.attentions.0"
+    b, c, h, w = x.shape
+    t = group_norm(sd, p + ".group_norm", x, groups, 1e-6).view(b, c, h * w).transpose(1, 2)
+    q, k, v = linear(sd, p + ".to_q", t), linear(sd, p + ".to_k", t), linear(sd, p + ".to_v", t)
+    a = ((q @ k.transpose(1, 2)) * c ** -0.5).softmax(-1) @ v
+    x = x + linear(sd, p + ".to_out.0", a).transpose(1, 2).reshape(b, c, h, w)
+    x = res("encoder.mid_block.resnets.1", x)
+    x = F.silu(group_norm(sd, "encoder.conv_norm_out", x, groups, 1e-6))
+    return conv2d(sd, "quant_conv", conv2d(sd, "encoder.conv_out", x), padding=0)
+

@@ -69,7 +69,7 @@ def case_unet3d(name, chans, Fr, h, w, timestep, seeds=(101, 102, 103)):
     print(f"{name}: out {tuple(out.shape)} |out|={out.norm():.4f} in {time.time() - t0:.1f}s")
 
 
-PIPE_SMALL = dict(chans=(64, 128, 256, 256), vae_chans=(32, 64, 128, 128), size=128, L=20, steps=3, guidance=3.5,
+PIPE_SMALL = dict(chans=(64, 128, 256, 256), vae_chans=(64, 64, 128, 128), size=128, L=20, steps=3, guidance=3.5,
                   seeds=dict(unet3d=301, unet2d=302, pose=303, vae=304, clip=305, inputs=306, latents=42))
 SCHED_KWARGS = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", clip_sample=False, steps_offset=1,
                     prediction_type="v_prediction", rescale_betas_zero_snr=True, timestep_spacing="trailing")

@@ -75,6 +75,17 @@ def small_clip_encoder(seed):
     return m.eval()
 
 
+def full_clip_encoder(seed):
+    """Must stay identical to oracle/make_golden.py::full_clip_encoder (CLIP ViT-L/14 vision tower, seeded weights)."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    cfg = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                           image_size=224, patch_size=14, projection_dim=768)
+    torch.manual_seed(seed)
+    m = CLIPVisionModelWithProjection(cfg)
+    m.load_state_dict(randomize_state_dict(m.state_dict(), seed=seed))
+    return m.eval()
+
+
 def pipeline_inputs(size, L, seed):
     import numpy as np
     import PIL.Image
@@ -111,7 +122,7 @@ def build_pipeline(P, device):
     pose.load_state_dict(randomize_state_dict(pose.state_dict(), seed=sd["pose"]))
     vae = AutoencoderKL(block_out_channels=tuple(P["vae_chans"]))
     vae.load_state_dict(randomize_state_dict(vae.state_dict(), seed=sd["vae"]))
-    clip = small_clip_encoder(sd["clip"])
+    clip = full_clip_encoder(sd["clip"]) if P.get("clip") == "vit_l_14" else small_clip_encoder(sd["clip"])
     pipe = Pose2VideoPipeline(vae=vae, image_encoder=clip, reference_unet=unet2d, denoising_unet=unet3d,
                               pose_guider=pose, scheduler=DDIMScheduler(**SCHED_KWARGS))
     return pipe.to(device, dtype=torch.float16)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 17
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/aniportrait_b200.h but not exported"
-    assert lib.ap_version() == 100
+    assert lib.ap_version() == 200
 
 
 def test_ops_refuse_cpu_tensors():

@@ -129,3 +129,18 @@ def test_vae_decode():
         ref = vae.decode(z).sample
         ours = OF.vae_decode(sd, z)
     assert rel_l2(ours, ref) < 1e-5
+
+
+def test_vae_encode():
+    ref_import.activate()
+    from diffusers import AutoencoderKL
+    vae = AutoencoderKL(block_out_channels=(32, 64, 128, 128))
+    sd = _load(vae, 10)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(2, 3, 64, 48, generator=g) * 2 - 1
+    with torch.no_grad():
+        dist = vae.encode(x).latent_dist
+        ours = OF.vae_encode(sd, x)
+    assert ours.shape == (2, 8, 8, 6)
+    assert rel_l2(ours[:, :4], dist.mean) < 1e-5
+    assert rel_l2(ours, torch.cat([dist.mean, dist.logvar], 1)) < 1e-5

@@ -1,0 +1,126 @@
+"""PoseGuider on the sm_100a kernels (direct small-channel convolutions, tcgen05 implicit-GEMM 3x3 convolutions, train-mode
+BatchNorm + ReLU, self-attention blocks) against torch fp32 evaluations of the same ops and against the CPU oracle
+(oracle/functional.py::pose_guider_forward, pinned to the unmodified reference by tests/test_oracle_vs_reference.py).
+Reference: src/models/pose_guider.py:14-162. Tolerance 1e-2 rel-L2 (north_star); op tests 2e-3."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, dev, scale, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev, torch.float16)
+
+
+@pytest.mark.parametrize("rows,c", [(4 * 512 * 512, 8), (3 * 64 * 64, 320), (5 * 8 * 8 + 3, 1280), (1000, 16)])
+def test_batchnorm_train_relu(cuda_dev, rows, c):
+    from aniportrait_b200 import ops
+    x = _mk((rows, c), cuda_dev, 30.0, 1) + 7.0
+    gamma = torch.randn(c, generator=torch.Generator().manual_seed(2)).to(cuda_dev)
+    beta = torch.randn(c, generator=torch.Generator().manual_seed(3)).to(cuda_dev)
+    y = ops.batch_norm_train(x, gamma, beta, 1e-5, relu=True)
+    ref = F.relu(F.batch_norm(x.float().t().unsqueeze(0), None, None, gamma, beta, training=True, momentum=0.0,
+                              eps=1e-5))[0].t()
+    assert rel_l2(y, ref) < 2e-3
+    y2 = ops.batch_norm_train(x, gamma, beta, 1e-5, relu=True)
+    assert torch.equal(y, y2), "order-fixed reduction must be bit-reproducible"
+    y3 = ops.batch_norm_train(x, gamma, beta, 1e-5, relu=False)
+    ref3 = F.batch_norm(x.float().t().unsqueeze(0), None, None, gamma, beta, training=True, momentum=0.0, eps=1e-5)[0].t()
+    assert rel_l2(y3, ref3) < 2e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,s,h,w", [(3, 3, 3, 1, 64, 48), (3, 16, 4, 2, 64, 48), (16, 16, 3, 1, 40, 24),
+                                             (16, 32, 4, 2, 40, 24), (32, 32, 3, 1, 24, 16), (32, 64, 4, 2, 24, 16)])
+def test_conv2d_direct(cuda_dev, cin, cout, k, s, h, w):
+    from aniportrait_b200 import ops
+    nf = 3
+    g = torch.Generator().manual_seed(10 + cin + cout)
+    x = torch.randn(nf, cin, h, w, generator=g).to(cuda_dev, torch.float16)
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (k * k * cin)) ** 0.5).to(cuda_dev, torch.float16)
+    b = torch.randn(cout, generator=g).to(cuda_dev)
+    cin_p = (cin + 7) // 8 * 8
+    cout_p = 8 if cout <= 8 else (cout + 15) // 16 * 16
+    xp = torch.zeros(nf, h, w, cin_p, dtype=torch.float16, device=cuda_dev)
+    xp[..., :cin] = x.permute(0, 2, 3, 1)
+    bp = torch.zeros(cout_p, device=cuda_dev)
+    bp[:cout] = b
+    y = ops.conv2d_direct(xp, ops.pack_conv_direct_weight(wt, cin_p, cout_p), s, 1, bias=bp)
+    ref = F.conv2d(x.float(), wt.float(), b, stride=s, padding=1).permute(0, 2, 3, 1)
+    assert y.shape == (nf, ref.shape[1], ref.shape[2], cout_p)
+    assert rel_l2(y[..., :cout], ref) < 2e-3
+    assert y[..., cout:].abs().max().item() == 0 if cout_p > cout else True
+
+
+def _build(c0, seed, dev):
+    from aniportrait_b200.models.pose_guider import PoseGuider
+    from aniportrait_b200.synthetic import randomize_state_dict
+    m = PoseGuider(c0)
+    sd = randomize_state_dict(m.state_dict(), seed=seed)
+    m.load_state_dict(sd)
+    return m.to(dev, torch.float16), sd
+
+
+def _pose_maps(frames, size, seed):
+    """What the scripts hand to the pipeline (uint8 BGR maps with a few coloured segments) after the reference's
+    cond_image_processor: 2 * x - 1 WITHOUT /255 -> values in [-1, 509]."""
+    out = []
+    for f in range(frames):
+        r = np.random.RandomState(seed + f)
+        img = np.zeros((size, size, 3), dtype=np.uint8)
+        for _ in range(60):
+            x0, y0 = r.randint(0, size, 2)
+            ln = r.randint(8, size // 4)
+            col = r.randint(64, 256, 3)
+            if r.rand() < 0.5:
+                img[y0:y0 + 2, x0:min(size, x0 + ln)] = col
+            else:
+                img[y0:min(size, y0 + ln), x0:x0 + 2] = col
+        out.append(torch.from_numpy(img).permute(2, 0, 1).float() * 2.0 - 1.0)
+    return torch.stack(out)     # [frames, 3, H, W]
+
+
+@pytest.mark.parametrize("c0,frames,size", [(320, 4, 512), (64, 5, 128)])
+def test_pose_guider_against_oracle(cuda_dev, c0, frames, size):
+    """Full width at 512x512 with the real input range (the BASELINE geometry), train-mode BatchNorm over the window's
+    frames; and a reduced-width / odd frame count case."""
+    from aniportrait_b200 import ops
+    from oracle import functional as OF
+    pg, sd = _build(c0, 700 + c0, cuda_dev)
+    x = _pose_maps(frames, size, 900)
+    assert x.max() > 400
+    n0 = ops.KERNEL_LAUNCHES
+    fea = pg(x.permute(1, 0, 2, 3).unsqueeze(0).to(cuda_dev, torch.float16), None)
+    assert ops.KERNEL_LAUNCHES - n0 > 60
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        # the product feeds fp16 pose maps (as the reference pipeline does, pipeline_pose2vid_long.py:444-446)
+        ref = OF.pose_guider_forward(sd, x.half().float().permute(1, 0, 2, 3).unsqueeze(0), c0=c0)
+    assert len(fea) == 5
+    for k, (a, b) in enumerate(zip(fea, ref)):
+        assert a.shape == b.shape
+        err = rel_l2(a, b)
+        print(f"pose guider c0={c0} map {k} {tuple(a.shape)}: rel-L2 = {err:.3e}")
+        assert err < 1e-2, (k, err)
+
+
+def test_pose_guider_launches_only_library_kernels(cuda_dev):
+    """No cuDNN / ATen math in the PoseGuider: under the profiler every CUDA kernel of a forward_nhwc call is one of this
+    library's (namespace ap::) — layout / fill kernels of torch are not allowed either."""
+    pg, _ = _build(64, 5, cuda_dev)
+    x = _pose_maps(2, 128, 3).to(cuda_dev, torch.float16)
+    pg.forward_nhwc(x)
+    torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        pg.forward_nhwc(x)
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA
+             or getattr(e, "self_device_time_total", 0) > 0]
+    names = [n for n in names if "memcpy" not in n.lower() and "memset" not in n.lower()]
+    foreign = [n for n in names if "ap::" not in n]
+    assert names and not foreign, f"non-library kernels in the PoseGuider: {foreign}"
