@@ -67,7 +67,35 @@ struct AttnParams {
   float scale_log2;       // softmax scale * log2(e)
   __half* out;
   long long ldo;
+  int stagger_clk;        // v5: start-up delay of the softmax warps of every second CTA of an SM (see attention5_kernel)
 };
+
+// Row maximum with the 3-input FMNMX3 of sm_100 (half the instructions of a 2-input reduction).
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+template <int N>
+__device__ __forceinline__ float row_max(const uint32_t* sr) {
+  static_assert(N % 32 == 0, "row length");
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    m[i] = fmax3(__uint_as_float(sr[i]), __uint_as_float(sr[8 + i]), __uint_as_float(sr[16 + i]));
+#pragma unroll
+  for (int i = 24; i + 16 <= N; i += 16)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmax3(m[j], __uint_as_float(sr[i + j]), __uint_as_float(sr[i + 8 + j]));
+  if ((N - 24) % 16 != 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __uint_as_float(sr[N - 8 + j]));
+  }
+  return fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]), fmaxf(m[6], m[7]));
+}
+
+// Per-SM arrival counter of attention5 CTAs (two are co-resident per SM; parity = which of the two a CTA is).
+__device__ unsigned int g_attn5_sm_arrivals[1024];
 
 template <int DPAD, int BN>
 struct AttnCfg {
@@ -739,6 +767,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* pv_done = p_full + 2;         // every P.V (rescale path only)
   uint64_t* o_done = pv_done + 1;         // last P.V of a unit
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint32_t* slot_ptr = tmem_ptr + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -761,6 +790,10 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(pv_done, 1);
     mbar_init(o_done, 1);
     fence_mbar_init();
+    // which of the SM's two co-resident CTAs is this one? (every launch adds exactly two arrivals per SM: parity is enough)
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    *slot_ptr = atomicAdd(&g_attn5_sm_arrivals[smid & 1023], 1u) & 1u;
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
@@ -870,6 +903,16 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t t_o = tmem_base + Cfg::TMEM_O + t_lane;
     uint32_t g = 0, uc = 0;
     uint32_t sr[BN];
+    // Anti-phase start. Per key tile a softmax warp spends ~2/3 of its time in the MUFU-bound exponential loop and ~1/3 in
+    // phases without exponentials (S load, row maximum, P store, barrier). The two CTAs of an SM run the same schedule on
+    // the same kind of unit; launched together they stay IN phase (the phase difference of two such warps sharing the MUFU
+    // pipe is neutrally stable), so their exponential loops collide and their idle phases coincide: XU pipe 70 % busy.
+    // Delaying the softmax warps of every second CTA by about one idle phase interleaves them instead.
+    if (p.stagger_clk > 0 && *slot_ptr != 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger_clk) {
+      }
+    }
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
       int frame, head, m_tile, T;
       decode(unit, frame, head, m_tile, T);
@@ -890,14 +933,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int i = 0; i < BN; ++i)
             if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
         }
-        float mx8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
-#pragma unroll
-        for (int i = 8; i < BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sr[i]));
-        float tmax = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                           fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        tmax *= p.scale_log2;
+        float tmax = row_max<BN>(sr) * p.scale_log2;
         float alpha = 1.f;
         bool need = false;
         if (j == 0) {
@@ -1053,6 +1089,8 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = (__half*)out;
   p.ldo = ldo;
+  static const int stagger_env = getenv("AP_ATTN_STAGGER") ? atoi(getenv("AP_ATTN_STAGGER")) : 700;
+  p.stagger_clk = stagger_env;
   if (has_bank) {
     const int max_bank = (n_frames - 1 - first_bank_frame) / frames_per_bank;
     AP_REQUIRE(first_bank_frame >= n_frames || max_bank < n_banks, "attention: bank index out of range");

@@ -48,6 +48,7 @@ struct GemmParams {
   // epilogue
   const float* bias;       // [groups, Nout] fp32 or null
   int bias_group_rows;     // rows sharing one bias row (>= M -> single row)
+  long long bias_ld;       // floats between bias rows (N unless several ops share one table)
   const __half* residual;  // [M, ldr] or null
   int ldr;
   __half* out;             // [M, ldo]
@@ -59,6 +60,22 @@ struct GemmParams {
   int sub_w, sub_h, sub_n; // conv modes: geometry of a warp's 32-row sub-box
   int debug;               // AP_GEMM_DEBUG: 1 = skip TMA loads (MMA pace), 2 = skip MMAs (TMA pace), 3 / 4 = skip every other
                            // B / A load (traffic sensitivity); results are garbage
+  // ---- statistics fused into the epilogue (TMA epilogue only) --------------------------------------------------------
+  // Producer side. Both are computed from the fp16-ROUNDED outputs (what the consumer will read) and written as per-warp
+  // partials in a fixed layout: no atomics, the consumer adds them in a fixed order (bit-reproducible).
+  float2* row_stat_out;    // LayerNorm of the NEXT op: {sum, sum of squares} of output row m over the columns this epilogue
+                           // warp handled: [part][row_stat_ld], part = 2 * (n-group of the work item) + (warp's column half)
+  long long row_stat_ld;
+  float2* col_stat_out;    // GroupNorm of the NEXT op: {sum, sumsq} per output column over the 32 rows of the warp's TMEM lane
+                           // quarter: [4 * m_tile + quarter][col_stat_ld]
+  long long col_stat_ld;
+  // Consumer side: this GEMM's A operand is x, its weights carry the LayerNorm scale (W' = W diag(gamma)); the epilogue
+  // turns acc = x.W'^T into LN(x).W^T = rstd (acc - mean colsum(W')) + (beta.W^T + b) [the last term arrives as `bias`].
+  const float2* ln_stat;   // [ln_parts][ln_stat_ld] row partials written by the producer of x
+  int ln_parts;
+  long long ln_stat_ld;
+  const float* ln_colsum;  // [N] fp32: sum_k W'[n, k]
+  float ln_inv_k, ln_eps;
 };
 
 // NACC = 2 ("wide" tile, cta_group::2 only): one staged A tile feeds TWO N = BN accumulators (two adjacent BN-wide weight
@@ -348,7 +365,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           m = ((long long)n * p.Ho + y) * p.Wo + x;
         }
         const float* bias_row = nullptr;
-        if (p.bias != nullptr) bias_row = p.bias + (row_ok ? (m / p.bias_group_rows) : 0) * (long long)p.N;
+        if (p.bias != nullptr) bias_row = p.bias + (row_ok ? (m / p.bias_group_rows) : 0) * p.bias_ld;
+        // LayerNorm folding (consumer): row statistics from the producer's partials, summed in a fixed order
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (p.ln_stat != nullptr) {
+          float S = 0.f, Q = 0.f;
+          if (row_ok)
+            for (int i = 0; i < p.ln_parts; ++i) {
+              const float2 t = __ldg(p.ln_stat + (long long)i * p.ln_stat_ld + m);
+              S += t.x;
+              Q += t.y;
+            }
+          ln_mean = S * p.ln_inv_k;
+          ln_rstd = rsqrtf(fmaxf(Q * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+        }
+        float rs_s = 0.f, rs_q = 0.f;   // producer: this warp's share of the row's {sum, sumsq}
+        const bool want_stats = (EPI == EPI_LINEAR) && (p.row_stat_out != nullptr || p.col_stat_out != nullptr);
         auto load_res = [&](int chunk) {
           if (lane == 0) {
             mbar_arrive_expect_tx(rbar, 2048);
@@ -398,6 +430,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                   bg[4 * j] = g.x; bg[4 * j + 1] = g.y; bg[4 * j + 2] = g.z; bg[4 * j + 3] = g.w;
                 }
               }
+              if (p.ln_stat != nullptr) {   // acc -> rstd (acc - mean colsum) for the value and the gate columns
+                const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + acol + h * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 cs = __ldg(c4 + j);
+                  const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    r[h * 32 + 4 * j + t] = __float_as_uint(
+                        ln_rstd * (__uint_as_float(r[h * 32 + 4 * j + t]) - ln_mean * cc[t]));
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 v[h * 16 + j] = (__uint_as_float(r[h * 32 + j]) + bv[j]) *
@@ -409,6 +453,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.ln_stat != nullptr) {
+              const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + acol);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 cs = __ldg(c4 + j);
+                v[4 * j + 0] = ln_rstd * (v[4 * j + 0] - ln_mean * cs.x);
+                v[4 * j + 1] = ln_rstd * (v[4 * j + 1] - ln_mean * cs.y);
+                v[4 * j + 2] = ln_rstd * (v[4 * j + 2] - ln_mean * cs.z);
+                v[4 * j + 3] = ln_rstd * (v[4 * j + 3] - ln_mean * cs.w);
+              }
+            }
             if (bias_row != nullptr) {
               const float4* b4 = reinterpret_cast<const float4*>(bias_row + acol);
 #pragma unroll
@@ -436,15 +491,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
           // the previous TMA store out of obuf must have finished reading it
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
+          if (want_stats && !row_ok) {   // rows past the end of the tensor are clipped by the store; keep them out of the sums
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             __half2 o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+            if (EPI == EPI_LINEAR && p.row_stat_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(o[j]);
+                rs_s += f.x + f.y;
+                rs_q = fmaf(f.x, f.x, fmaf(f.y, f.y, rs_q));
+              }
+            }
             *reinterpret_cast<uint4*>(obuf + lane * 64 + ((q ^ sw) << 4)) = *reinterpret_cast<uint4*>(o);
           }
           fence_proxy_async_smem();
           __syncwarp();
+          if (EPI == EPI_LINEAR && p.col_stat_out != nullptr) {
+            // column sums over the 32 rows of this warp's box, read back from the staged fp16 tile: lane = (row parity,
+            // half2 column), 16 conflict-free 4-byte loads per lane, then the two row parities are added
+            const int hc = lane & 15, rp = lane >> 4;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int rw = 2 * rr + rp;
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(
+                  obuf + rw * 64 + ((((hc >> 2) ^ ((rw >> 1) & 3))) << 4) + ((hc & 3) << 2));
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+              s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+              s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+            if (lane < 16) {
+              float4* dst = reinterpret_cast<float4*>(p.col_stat_out + (long long)(m_tile * 4 + lane_group) * p.col_stat_ld +
+                                                      n_tile * BN + c * 32 + 2 * hc);
+              *dst = make_float4(s0, q0, s1, q1);
+            }
+          }
           if (has_res && c + 2 < NACC * NCHUNK) load_res(c + 2);      // rbuf fully consumed by every lane (syncwarp above)
           if (lane == 0) {
             const int ocol = n_tile * (BN / (EPI == EPI_GEGLU ? 2 : 1)) + c * 32;
@@ -455,6 +546,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         }
         if (NACC == 2 && !released0) release(s0);
         release(s1);
+        if (EPI == EPI_LINEAR && p.row_stat_out != nullptr && row_ok)
+          p.row_stat_out[(long long)(2 * (tile % n_groups) + col_half) * p.row_stat_ld + m] = make_float2(rs_s, rs_q);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) tma_store_wait_all<0>();   // stores must complete before the CTA (and its smem) goes away
@@ -481,7 +574,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       const float* bias_row = nullptr;
       if (p.bias != nullptr) {
         const long long g = row_ok ? (m / p.bias_group_rows) : 0;
-        bias_row = p.bias + g * (long long)(EPI == EPI_GEGLU ? p.N : p.N);
+        bias_row = p.bias + g * p.bias_ld;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -722,14 +815,65 @@ static int make_weight_map(CUtensorMap* tm, const void* w, int N, long long K, i
   return encode_tmap(tm, w, 2, dims, strides, box, true);
 }
 
+// Validates and copies the optional epilogue extensions into the kernel parameters (after tma_epi / tile counts are known).
+static int apply_ext(GemmParams& p, const ap_epilogue_ext* ext, int epi, long long m_pad, int k_ln) {
+  p.bias_ld = p.N;
+  if (ext == nullptr) return AP_OK;
+  if (ext->bias_ld > 0) p.bias_ld = ext->bias_ld;
+  const bool any = ext->row_stat_out || ext->col_stat_out || ext->ln_stat;
+  if (!any) return AP_OK;
+  if (!p.tma_epi) return fail(AP_ERR_INVALID, "gemm: epilogue statistics / LayerNorm folding need the TMA epilogue (aligned fp16 out)");
+  if (ext->row_stat_out) {
+    if (epi != EPI_LINEAR) return fail(AP_ERR_INVALID, "gemm: row statistics are not available with GEGLU");
+    if (ext->row_stat_ld < m_pad) return fail(AP_ERR_INVALID, "gemm: row_stat_ld %lld < padded M %lld", ext->row_stat_ld, m_pad);
+    if (p.a_mode != A_GEMM) return fail(AP_ERR_INVALID, "gemm: row statistics only for plain GEMMs");
+    p.row_stat_out = (float2*)ext->row_stat_out;
+    p.row_stat_ld = ext->row_stat_ld;
+  }
+  if (ext->col_stat_out) {
+    if (epi != EPI_LINEAR) return fail(AP_ERR_INVALID, "gemm: column statistics are not available with GEGLU");
+    if (ext->col_stat_ld < p.N || (ext->col_stat_ld & 1)) return fail(AP_ERR_INVALID, "gemm: bad col_stat_ld %lld", ext->col_stat_ld);
+    if ((reinterpret_cast<uintptr_t>(ext->col_stat_out) & 15) != 0) return fail(AP_ERR_INVALID, "gemm: col_stat_out must be 16-byte aligned");
+    if (p.a_mode != A_GEMM && p.sub_n != 1)
+      return fail(AP_ERR_INVALID, "conv3x3: column statistics need Ho*Wo %% 32 == 0 with 32-row sub-boxes inside one frame");
+    p.col_stat_out = (float2*)ext->col_stat_out;
+    p.col_stat_ld = ext->col_stat_ld;
+  }
+  if (ext->ln_stat) {
+    if (p.a_mode != A_GEMM) return fail(AP_ERR_INVALID, "gemm: LayerNorm folding only for plain GEMMs");
+    if (!ext->ln_colsum || ext->ln_parts <= 0 || ext->ln_stat_ld < m_pad)
+      return fail(AP_ERR_INVALID, "gemm: bad LayerNorm-folding arguments (parts=%d, ld=%lld)", ext->ln_parts, ext->ln_stat_ld);
+    p.ln_stat = (const float2*)ext->ln_stat;
+    p.ln_parts = ext->ln_parts;
+    p.ln_stat_ld = ext->ln_stat_ld;
+    p.ln_colsum = ext->ln_colsum;
+    p.ln_inv_k = 1.f / (float)k_ln;
+    p.ln_eps = ext->ln_eps;
+  }
+  return AP_OK;
+}
+
 }  // namespace ap
 
 using namespace ap;
 
+extern "C" int ap_gemm_row_stat_parts(long long M, int N, int K, int flags, int block_n) {
+  const int epi = (flags & AP_GEMM_GEGLU) ? EPI_GEGLU : EPI_LINEAR;
+  const int bn = pick_bn(N, block_n, (M + 127) / 128, epi == EPI_GEGLU);
+  if (bn <= 0 || N % bn != 0) return fail(AP_ERR_INVALID, "gemm: N=%d not tileable (block_n=%d)", N, block_n);
+  GemmParams p{};
+  p.num_m_tiles = (int)((M + 127) / 128);
+  p.num_n_tiles = N / bn;
+  p.num_kb = (K + 63) / 64;
+  p.tma_epi = 1;
+  const int cg = pick_cg(bn, p.num_m_tiles, p.num_n_tiles);
+  return p.num_n_tiles / (pick_wide(bn, epi, cg, p) ? 2 : 1);
+}
+
 extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2, long long lda2, int K2,
                            const void* w, long long M, int N, const float* bias, long long bias_group_rows,
                            const void* residual, long long ldr, void* out, long long ldo, int n_valid, int flags,
-                           int block_n, void* stream) {
+                           int block_n, void* stream, const ap_epilogue_ext* ext) {
   AP_REQUIRE(a && w && out, "gemm: null pointer");
   AP_REQUIRE(M > 0 && N > 0 && K1 > 0, "gemm: bad shape M=%lld N=%d K1=%d", M, N, K1);
   AP_REQUIRE(K1 % 64 == 0 || (a2 == nullptr), "gemm: K1 must be a multiple of 64 when a second source follows");
@@ -798,6 +942,8 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
     }
     p.tma_epi = 1;
   }
+  if ((rc = apply_ext(p, ext, epi, (long long)p.num_m_tiles * 128, K1))) return rc;
+  if (ext && ext->ln_stat) AP_REQUIRE(a2 == nullptr, "gemm: LayerNorm folding with a two-source A is not supported");
   return dispatch(bn, epi, cg, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }
 
@@ -805,7 +951,7 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
 extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int H, int W, int stride,
                                    const void* w, int Cout, const float* bias, long long bias_group_rows,
                                    const void* residual, void* out, long long ldo, int n_valid, int block_n,
-                                   void* stream) {
+                                   void* stream, const ap_epilogue_ext* ext) {
   AP_REQUIRE(x && w && out, "conv3x3: null pointer");
   AP_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
   AP_REQUIRE(C1 % 64 == 0 && (x2 == nullptr || C2 % 64 == 0), "conv3x3: channels must be multiples of 64 (pad)");
@@ -885,5 +1031,10 @@ extern "C" int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2
     if (residual && (rc = encode_tmap(&tmRes, residual, 4, dims, so, box, false, 2, 64))) return rc;
     p.tma_epi = 1;
   }
+  if ((rc = apply_ext(p, ext, EPI_LINEAR, (long long)p.num_m_tiles * 128, 0))) return rc;
+  // entry e of the partials must belong to frame e / (Ho*Wo/32): tiles inside one frame, or whole frames per tile
+  if (p.col_stat_out)
+    AP_REQUIRE((Ho * Wo) % 32 == 0 && (p.bn == 1 || p.tiles_x * p.tiles_y == 1),
+               "conv3x3: column statistics need Ho*Wo %% 32 == 0 and frame-major 32-row sub-boxes (Ho=%d Wo=%d)", Ho, Wo);
   return dispatch(bn_, EPI_LINEAR, cg, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }

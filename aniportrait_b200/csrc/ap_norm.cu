@@ -107,6 +107,37 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ p0, int chunks0, i
   }
 }
 
+// Finalize from PER-COLUMN partials written by the producing GEMM / conv epilogue (ap_gemm.cu: col_stat_out): entry e holds
+// {sum, sumsq} of every output channel over rows [32 e, 32 e + 32) of the producer's output, i.e. frame e / (HW / 32).
+// One warp per group (grid Nf, block 32 * G): lanes stride over (entry, channel of the group), double accumulation in a
+// fixed order, xor-shuffle tree -> stats[frame][group] = {mean, rstd}. The group may straddle the two concatenated sources.
+__global__ void gn_finalize_cols_kernel(const float2* __restrict__ p0, long long ld0, int C1,
+                                        const float2* __restrict__ p1, long long ld1, int epf, int cpg, int G,
+                                        double inv_count, float eps, float2* __restrict__ stats) {
+  const int frame = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0.0, q = 0.0;
+  const int total = epf * cpg;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int e = idx / cpg;
+    const int c = g * cpg + idx % cpg;
+    const long long row = (long long)frame * epf + e;
+    const float2 v = c < C1 ? __ldg(p0 + row * ld0 + c) : __ldg(p1 + row * ld1 + (c - C1));
+    s += v.x;
+    q += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s * inv_count;
+    const double var = fmax(q * inv_count - mean * mean, 0.0);
+    stats[(long long)frame * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+}
+
 // x * sigmoid(x) with two MUFU ops (ex2, rcp) and no IEEE-division sequence: the SiLU variant of gn_apply was ALU-bound
 // (47 us against 25 us without SiLU at 32 x 4096 x 320), not HBM-bound. Relative error ~2^-22, far below fp16 resolution.
 __device__ __forceinline__ float silu_fast(float v) {
@@ -410,6 +441,40 @@ extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int 
       gn_apply_kernel<false><<<dim3(chunks[s], Nf), threads[s], 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
                                                                              cpg, rpb[s], stat2, groups, gamma, beta,
                                                                              (__half*)out);
+  }
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+// GroupNorm whose statistics come from the producers' epilogues: finalize (column partials -> {mean, rstd}) + apply.
+extern "C" int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* colstat1, long long ld1, const void* x2,
+                                           int C2, const void* colstat2, long long ld2, int Nf, int HW, int groups,
+                                           float eps, const float* gamma, const float* beta, int silu, float* stats,
+                                           void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int C = C1 + (x2 ? C2 : 0);
+  AP_REQUIRE(x && out && stats && gamma && beta && colstat1 && (!x2 || colstat2), "groupnorm_apply: null pointer");
+  AP_REQUIRE(C % groups == 0 && groups <= 32, "groupnorm_apply: C=%d groups=%d (at most 32 groups)", C, groups);
+  AP_REQUIRE(C1 % 8 == 0 && (!x2 || C2 % 8 == 0), "groupnorm_apply: channel counts must be multiples of 8");
+  AP_REQUIRE(HW % 32 == 0, "groupnorm_apply: HW=%d must be a multiple of 32 (32-row statistics entries)", HW);
+  AP_REQUIRE(ld1 >= C1 && (!x2 || ld2 >= C2), "groupnorm_apply: partial row stride smaller than the channel count");
+  const int cpg = C / groups;
+  float2* stat2 = reinterpret_cast<float2*>(stats);
+  gn_finalize_cols_kernel<<<Nf, 32 * groups, 0, stream>>>((const float2*)colstat1, ld1, C1, (const float2*)colstat2, ld2,
+                                                          HW / 32, cpg, groups, 1.0 / ((double)HW * (double)cpg), eps, stat2);
+  AP_CHECK_CUDA(cudaGetLastError());
+  const void* srcs[2] = {x, x2};
+  const int cs[2] = {C1, C2};
+  const int offs[2] = {0, C1};
+  for (int s = 0; s < (x2 ? 2 : 1); ++s) {
+    int threads, rpb, chunks;
+    gn_launch_geometry(HW, cs[s], Nf, &threads, &rpb, &chunks);
+    if (silu)
+      gn_apply_kernel<true><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
+                                                                      stat2, groups, gamma, beta, (__half*)out);
+    else
+      gn_apply_kernel<false><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
+                                                                       stat2, groups, gamma, beta, (__half*)out);
   }
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;

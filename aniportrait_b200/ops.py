@@ -60,10 +60,75 @@ def interleave_geglu(w: torch.Tensor, b: torch.Tensor | None):
 # --------------------------------------------------------------------------------------------------------------
 # GEMM / conv
 # --------------------------------------------------------------------------------------------------------------
+class RowStats:
+    """Per-row {sum, sumsq} partials of a GEMM output, written by its epilogue: the LayerNorm statistics of the next op."""
+
+    def __init__(self, buf: torch.Tensor, parts: int, ld: int):
+        self.buf, self.parts, self.ld = buf, parts, ld
+
+
+class ColStats:
+    """Per-channel {sum, sumsq} partials over 32-row blocks of a GEMM / conv output: the GroupNorm statistics of the next
+    op. buf: fp32 [entries, C, 2]."""
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+
+
+class LNFold:
+    """LayerNorm folded into the consuming GEMM: its weights are W diag(gamma), its bias beta.W^T + b, and the epilogue
+    applies rstd (acc - mean colsum) with the row statistics `stats` of the A operand."""
+
+    def __init__(self, stats: RowStats, colsum: torch.Tensor, eps: float = 1e-5):
+        self.stats, self.colsum, self.eps = stats, colsum, eps
+
+
+def _epilogue_ext(M, N, device, row_stats, col_stats, ln, bias, flags, K, block_n):
+    """Builds the ap_epilogue_ext for a call; returns (ext | None, RowStats | None, ColStats | None)."""
+    bias_ld = 0
+    if bias is not None and bias.dim() == 2 and bias.stride(0) != bias.shape[1]:
+        bias_ld = bias.stride(0)           # a column slice of a wider table shared by several ops
+    if not (row_stats or col_stats or ln is not None or bias_ld):
+        return None, None, None
+    ext = _lib.EpilogueExt()
+    m_pad = (M + 127) // 128 * 128
+    rs = cs = None
+    if row_stats:
+        parts = lib().ap_gemm_row_stat_parts(LL(M), I(N), I(K), I(flags), I(block_n))
+        if parts <= 0:
+            check(parts if parts < 0 else -1, "ap_gemm_row_stat_parts")
+        rs = RowStats(torch.empty(2 * parts, m_pad, 2, dtype=torch.float32, device=device), 2 * parts, m_pad)
+        ext.row_stat_out, ext.row_stat_ld = rs.buf.data_ptr(), m_pad
+    if col_stats:
+        cs = ColStats(torch.empty(m_pad // 32, N, 2, dtype=torch.float32, device=device))
+        ext.col_stat_out, ext.col_stat_ld = cs.buf.data_ptr(), N
+    if ln is not None:
+        assert ln.colsum.dtype == torch.float32 and ln.colsum.is_contiguous() and ln.colsum.numel() == N
+        assert ln.stats.ld >= m_pad
+        ext.ln_stat, ext.ln_parts, ext.ln_stat_ld = ln.stats.buf.data_ptr(), ln.stats.parts, ln.stats.ld
+        ext.ln_colsum, ext.ln_eps = ln.colsum.data_ptr(), ln.eps
+    ext.bias_ld = bias_ld
+    return ext, rs, cs
+
+
+def _with_stats(out, rs, cs, row_stats, col_stats):
+    if not (row_stats or col_stats):
+        return out
+    res = [out]
+    if row_stats:
+        res.append(rs)
+    if col_stats:
+        res.append(cs)
+    return tuple(res)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
          a2: torch.Tensor | None = None, geglu: bool = False, out: torch.Tensor | None = None,
-         bias_group_rows: int = 0, n_valid: int = 0, block_n: int = 0, out_f32: bool = False) -> torch.Tensor:
-    """out = [a | a2] @ w.T (+bias) (+residual); a:[M,K1] fp16 (row stride may exceed K1), w:[N,K1+K2] fp16."""
+         bias_group_rows: int = 0, n_valid: int = 0, block_n: int = 0, out_f32: bool = False,
+         row_stats: bool = False, col_stats: bool = False, ln: LNFold | None = None):
+    """out = [a | a2] @ w.T (+bias) (+residual); a:[M,K1] fp16 (row stride may exceed K1), w:[N,K1+K2] fp16.
+    row_stats / col_stats: also return the epilogue's RowStats / ColStats of `out` (-> (out, RowStats?, ColStats?)).
+    ln: fold a LayerNorm of `a` into this GEMM (see LNFold). bias may be a column slice of a wider fp32 table."""
     _ensure(a)
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.is_contiguous()
@@ -81,25 +146,56 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
         out = torch.empty(M, nout, dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
     assert out.stride(1) == 1 and out.dtype == (torch.float32 if out_f32 else torch.float16)
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape[-1] == N
+        assert bias.dtype == torch.float32 and bias.stride(-1) == 1 and bias.shape[-1] == N
+        assert bias.is_contiguous() or bias.dim() == 2
     if residual is not None:
         assert residual.dtype == torch.float16 and residual.stride(1) == 1 and residual.shape[0] == M
+    flags = (1 if geglu else 0) | (2 if out_f32 else 0)
+    ext, rs, cs = _epilogue_ext(M, N, a.device, row_stats, col_stats, ln, bias, flags, K1 + K2, block_n)
     rc = lib().ap_gemm_f16(ptr(a), LL(a.stride(0)), I(K1), ptr(a2), LL(a2.stride(0) if a2 is not None else 0), I(K2),
                            ptr(w), LL(M), I(N), fptr(bias), LL(bias_group_rows), ptr(residual),
                            LL(residual.stride(0) if residual is not None else 0), ptr(out), LL(out.stride(0)),
-                           I(nout), I((1 if geglu else 0) | (2 if out_f32 else 0)), I(block_n), stream_ptr())
+                           I(nout), I(flags), I(block_n), stream_ptr(), _lib.ext_ptr(ext))
     check(rc, "ap_gemm_f16")
     if SHAPE_LOG is not None:
         SHAPE_LOG.append(("gemm_geglu" if geglu else "gemm", M, N, K1 + K2, int(residual is not None)))
     _count()
-    return out
+    return _with_stats(out, rs, cs, row_stats, col_stats)
+
+
+def conv_col_stats_ok(nf: int, ho: int, wo: int) -> bool:
+    """Can a 3x3 conv with this output grid emit GroupNorm column statistics from its epilogue? (mirrors the tile-box choice
+    of ap_conv3x3_nhwc_f16: every 32-row sub-box of a tile must lie in one frame, entries frame-major)."""
+    def pow2_div(v, cap):
+        d = 1
+        while d * 2 <= cap and v % (d * 2) == 0:
+            d *= 2
+        return d
+    bw = pow2_div(wo, 128)
+    bh = pow2_div(ho, 128 // bw)
+    bnf = 128 // (bw * bh)
+    tiles = (wo // bw) * (ho // bh)
+    return (ho * wo) % 32 == 0 and bw * bh >= 32 and (bnf == 1 or tiles == 1)
+
+
+def conv_m_tiles(nf: int, ho: int, wo: int) -> int:
+    def pow2_div(v, cap):
+        d = 1
+        while d * 2 <= cap and v % (d * 2) == 0:
+            d *= 2
+        return d
+    bw = pow2_div(wo, 128)
+    bh = pow2_div(ho, 128 // bw)
+    bnf = 128 // (bw * bh)
+    return (nf + bnf - 1) // bnf * (wo // bw) * (ho // bh)
 
 
 def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, cout: int, bias: torch.Tensor | None = None,
             residual: torch.Tensor | None = None, x2: torch.Tensor | None = None, stride: int = 1,
-            out: torch.Tensor | None = None, bias_group_rows: int = 0, block_n: int = 0) -> torch.Tensor:
+            out: torch.Tensor | None = None, bias_group_rows: int = 0, block_n: int = 0, col_stats: bool = False):
     """x: [Nf, H, W, C1] fp16 channels-last (C1 % 64 == 0); w_packed: pack_conv3x3_weight(...); returns
-    [Nf, H/stride, W/stride, cout]."""
+    [Nf, H/stride, W/stride, cout] (and, with col_stats, the ColStats of the output for the next GroupNorm: only where
+    conv_col_stats_ok(...) holds). bias may be a column slice of a wider fp32 table."""
     _ensure(x)
     assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 4
     nf, h, wd, c1 = x.shape
@@ -114,17 +210,27 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, cout: int, bias: torch.Tens
         out = torch.empty(nf, ho, wo, cout, dtype=torch.float16, device=x.device)
     assert out.is_contiguous()
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape[-1] == cout_p
+        assert bias.dtype == torch.float32 and bias.stride(-1) == 1 and bias.shape[-1] == cout_p
+        assert bias.is_contiguous() or bias.dim() == 2
     if residual is not None:
         assert residual.is_contiguous() and residual.shape == out.shape
+    ext, cs = None, None
+    bias_ld = bias.stride(0) if (bias is not None and bias.dim() == 2 and bias.stride(0) != bias.shape[1]) else 0
+    if col_stats or bias_ld:
+        ext = _lib.EpilogueExt()
+        ext.bias_ld = bias_ld
+        if col_stats:
+            assert cout == cout_p, "column statistics need an unpadded output width"
+            cs = ColStats(torch.empty(4 * conv_m_tiles(nf, ho, wo), cout, 2, dtype=torch.float32, device=x.device))
+            ext.col_stat_out, ext.col_stat_ld = cs.buf.data_ptr(), cout
     rc = lib().ap_conv3x3_nhwc_f16(ptr(x), I(c1), ptr(x2), I(c2), I(nf), I(h), I(wd), I(stride), ptr(w_packed),
                                    I(cout_p), fptr(bias), LL(bias_group_rows), ptr(residual), ptr(out), LL(cout),
-                                   I(cout), I(block_n), stream_ptr())
+                                   I(cout), I(block_n), stream_ptr(), _lib.ext_ptr(ext))
     check(rc, "ap_conv3x3_nhwc_f16")
     if SHAPE_LOG is not None:
         SHAPE_LOG.append((f"conv3x3_s{stride}", nf * ho * wo, cout_p, 9 * (c1 + c2), int(residual is not None)))
     _count()
-    return out
+    return (out, cs) if col_stats else out
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -144,8 +250,11 @@ def _stats_workspace(device, n):
 
 
 def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
-               x2: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """x: [Nf, HW, C1] (or [Nf,H,W,C1]) fp16 channels-last; optional x2 concatenated along C. gamma/beta fp32 [C]."""
+               x2: torch.Tensor | None = None, out: torch.Tensor | None = None, stats: ColStats | None = None,
+               stats2: ColStats | None = None) -> torch.Tensor:
+    """x: [Nf, HW, C1] (or [Nf,H,W,C1]) fp16 channels-last; optional x2 concatenated along C. gamma/beta fp32 [C].
+    stats / stats2: ColStats written by the epilogue of the op that produced x / x2: when every source has them, the
+    statistics pass over the activation is skipped (finalize from the partials + apply only)."""
     _ensure(x)
     assert x.dtype == torch.float16 and x.is_contiguous()
     nf, c1 = x.shape[0], x.shape[-1]
@@ -158,7 +267,20 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     assert gamma.dtype == torch.float32 and gamma.numel() == c and beta.numel() == c
     if out is None:
         out = torch.empty(*x.shape[:-1], c, dtype=torch.float16, device=x.device)
-    stats = _stats_workspace(x.device, 2 * groups * (nf + 2 * GN_MAX_BLOCKS))
+    fused = stats is not None and (x2 is None or stats2 is not None) and hw % 32 == 0 and groups <= 32
+    ws = _stats_workspace(x.device, 2 * groups * (nf + 2 * GN_MAX_BLOCKS))
+    if fused:
+        for st, cc in ((stats, c1), (stats2, c2)):
+            if st is not None:
+                assert st.buf.shape[1] == cc and st.buf.shape[0] >= nf * hw // 32, (st.buf.shape, nf, hw, cc)
+        rc = lib().ap_groupnorm_apply_nhwc_f16(ptr(x), I(c1), ptr(stats.buf), LL(c1), ptr(x2), I(c2),
+                                               ptr(stats2.buf if stats2 is not None else None), LL(c2), I(nf), I(hw),
+                                               I(groups), _lib.c_float(eps), fptr(gamma), fptr(beta),
+                                               I(1 if silu else 0), fptr(ws), ptr(out), stream_ptr())
+        check(rc, "ap_groupnorm_apply_nhwc_f16")
+        _count(3 if x2 is not None else 2)
+        return out
+    stats = ws
     rc = lib().ap_groupnorm_nhwc_f16(ptr(x), I(c1), ptr(x2), I(c2), I(nf), I(hw), I(groups), _lib.c_float(eps),
                                      fptr(gamma), fptr(beta), I(1 if silu else 0), fptr(stats), ptr(out),
                                      stream_ptr())

@@ -475,7 +475,7 @@ def run_product(args):
         value = world * L / (ms_step / 1e3)
         e2e_value = world * L / (e2e_ms / 1e3)
         h2d = int(len(poses) * H * W * 3 + 3 * 224 * 224 * 4 + 3 * H * W * 4 + 4 * L * (H // 8) * (W // 8) * 2)
-        d2h = int(3 * L * H * W * 2)
+        d2h = int(3 * L * H * W * 4)      # fp32 video, converted on the device, one pinned-buffer copy
         unet_ms = phases["denoise_ms"] / DDIM_STEPS
         unet_tflops = FLOP_UNET_CALL / unet_ms / 1e9
         line = {

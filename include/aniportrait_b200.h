@@ -31,6 +31,35 @@ extern "C" {
 #define AP_GEMM_GEGLU 1 /* weight rows interleaved [16 value | 16 gate]; out = value * gelu_erf(gate), N/2 columns */
 #define AP_GEMM_OUT_F32 2 /* `out` is fp32 [M, ldo] (used for the small per-step bias tables) */
 
+/*
+ * Optional epilogue extensions of ap_gemm_f16 / ap_conv3x3_nhwc_f16 (pass NULL for none). They need the TMA epilogue
+ * (16-byte aligned fp16 output with ldo % 8 == 0); the functions fail otherwise.
+ *
+ * Statistics for the NEXT normalisation, fused into this op's epilogue (reference: the standalone nn.LayerNorm /
+ * nn.GroupNorm passes of src/models/attention.py:331-362, motion_module.py:228-241, resnet.py:221-238): computed from the
+ * fp16-rounded outputs, written as per-warp partials in a fixed layout (no atomics; consumers add them in a fixed order).
+ *   row_stat_out  fp32 pairs {sum, sumsq} [parts][row_stat_ld]: output row m over the columns one epilogue warp handled;
+ *                 parts = 2 * ap_gemm_row_stat_parts(...) ; row_stat_ld >= M rounded up to 128
+ *   col_stat_out  fp32 pairs per output column over 32 consecutive rows: [ceil(M / 128) * 4][col_stat_ld]
+ *                 (conv: 32-row sub-boxes of the output tile; needs Ho * Wo % 32 == 0 so that no sub-box spans two frames)
+ * LayerNorm folded into this GEMM (the A operand is the un-normalised x, the weights are W diag(gamma), `bias` carries
+ * beta.W^T + b): out = rstd (acc - mean * ln_colsum) + bias with {mean, rstd} of row m from the partials `ln_stat`
+ * [ln_parts][ln_stat_ld] written by the producer of x, ln_colsum[n] = sum_k W'[n, k] (fp32), eps = ln_eps, K = K1.
+ *   bias_ld       row stride of the bias table in floats (0 = N): lets several ops share one [groups, sum of N] table
+ */
+typedef struct ap_epilogue_ext {
+  void* row_stat_out;
+  long long row_stat_ld;
+  void* col_stat_out;
+  long long col_stat_ld;
+  const void* ln_stat;
+  int ln_parts;
+  long long ln_stat_ld;
+  const float* ln_colsum;
+  float ln_eps;
+  long long bias_ld;
+} ap_epilogue_ext;
+
 int ap_version(void);
 const char* ap_last_error(void);
 /* Binds the library to `device` (cudaSetDevice), verifies sm_100, resolves the driver entry points it needs. */
@@ -49,7 +78,10 @@ int ap_init(int device);
  */
 int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2, long long lda2, int K2, const void* w,
                 long long M, int N, const float* bias, long long bias_group_rows, const void* residual,
-                long long ldr, void* out, long long ldo, int n_valid, int flags, int block_n, void* stream);
+                long long ldr, void* out, long long ldo, int n_valid, int flags, int block_n, void* stream,
+                const ap_epilogue_ext* ext);
+/* Number of n-groups (work items along N) ap_gemm_f16 will use for this shape: row_stat_out needs 2x this many parts. */
+int ap_gemm_row_stat_parts(long long M, int N, int K, int flags, int block_n);
 
 /*
  * 3x3 convolution, zero padding 1, stride 1|2, channels-last fp16, as an implicit GEMM (no im2col buffer).
@@ -60,7 +92,8 @@ int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2, long long 
  */
 int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int H, int W, int stride,
                         const void* w, int Cout, const float* bias, long long bias_group_rows,
-                        const void* residual, void* out, long long ldo, int n_valid, int block_n, void* stream);
+                        const void* residual, void* out, long long ldo, int n_valid, int block_n, void* stream,
+                        const ap_epilogue_ext* ext);
 
 /*
  * GroupNorm over channels-last activations, optional fused SiLU, optional second source concatenated along channels
@@ -74,6 +107,16 @@ int ap_conv3x3_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, i
 #define AP_GN_MAX_BLOCKS 2368
 int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf, int HW, int groups, float eps,
                           const float* gamma, const float* beta, int silu, float* stats, void* out, void* stream);
+
+/*
+ * The same GroupNorm with the statistics pass removed: {sum, sumsq} per channel and 32-row block were written by the
+ * epilogue of the op that produced x (ap_epilogue_ext.col_stat_out of ap_gemm_f16 / ap_conv3x3_nhwc_f16); this call only
+ * reduces them per (frame, group) and applies the normalisation. colstat*: fp32 pairs [Nf * HW / 32][ld*]; HW % 32 == 0,
+ * at most 32 groups. stats: fp32 workspace of 2 * groups * Nf floats.
+ */
+int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* colstat1, long long ld1, const void* x2, int C2,
+                                const void* colstat2, long long ld2, int Nf, int HW, int groups, float eps,
+                                const float* gamma, const float* beta, int silu, float* stats, void* out, void* stream);
 
 /*
  * LayerNorm over the last dim (+ optional additive table pe[(row / rows_per_pe) % pe_period][C], the motion module's
