@@ -14,15 +14,45 @@ import math
 import torch
 from torch import nn
 
+import os
+
 from .. import ops
 from .modeling import PackedCache, f16, f32
+
+# Normalisation fusion: LayerNorms are folded into the consuming GEMM (row statistics from the producer's
+# epilogue), GroupNorm statistics come from the producing conv / GEMM epilogue. AP_FUSE_NORMS=0 restores the standalone
+# LayerNorm / GroupNorm-statistics kernels (A/B timing, and the path the ReferenceNet write pass still needs for norm1).
+FUSE_NORMS = os.environ.get("AP_FUSE_NORMS", "1") != "0"
+
+
+def _cs(t):
+    """ColStats attached to an activation by the op that produced it (None: the GroupNorm runs its own statistics pass)."""
+    return getattr(t, "_ap_cs", None)
+
+
+def _tag(t, cs):
+    if cs is not None:
+        t._ap_cs = cs
+    return t
+
+
+def fold_layer_norm(w: torch.Tensor, b, gamma: torch.Tensor, beta: torch.Tensor):
+    """LN(x) W^T + b = rstd (x (W diag(gamma))^T - mean colsum) + (W beta + b). Returns (W' fp16, colsum fp32 of the ROUNDED
+    W', bias' fp32). w: [N, K] any dtype; b: [N] or None."""
+    w32 = w.detach().to(torch.float32)
+    wg = (w32 * gamma.detach().to(torch.float32)[None, :]).to(torch.float16).contiguous()
+    colsum = wg.to(torch.float32).sum(dim=1).contiguous()
+    bias = w32 @ beta.detach().to(torch.float32)
+    if b is not None:
+        bias = bias + b.detach().to(torch.float32)
+    return wg, colsum, bias.contiguous()
 
 
 class RunCtx:
     """Per-forward state threaded through the blocks."""
 
     def __init__(self, batch: int, frames: int, temb_act: torch.Tensor | None, ehs: torch.Tensor | None,
-                 ehs_key=None, ref_branch=None):
+                 ehs_key=None, ref_branch=None, emit_stats: bool = True, temb_bias=None):
         # ref_branch: None = the reference's layout (both CFG branches in the batch when the reader was built with
         # do_classifier_free_guidance); "uncond" / "cond" = this call carries ONE branch of a CFG reader (multi-GPU
         # (window, branch) work units): uncond never reads the bank, cond reads the conditional bank for every frame
@@ -35,6 +65,10 @@ class RunCtx:
         # (pipeline session). None = no caching (the constant is recomputed on every call): tensor addresses / versions
         # are NOT an identity — a fresh clone of another video's embedding routinely lands on the same address.
         self.ehs_key = ehs_key
+        # emit_stats: outputs of transformer / motion blocks feed a GroupNorm (UNets: yes; PoseGuider: no)
+        self.emit_stats = emit_stats and FUSE_NORMS
+        # temb_bias: {id(resnet): fp32 [B, cout] view}: every resnet's time-embedding bias from ONE GEMM per call
+        self.temb_bias = temb_bias
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -60,10 +94,25 @@ class FeedForward(nn.Module):
             return dict(w1=w1, b1=b1, w2=f16(self.net[2].weight), b2=f32(self.net[2].bias))
         return self._pk.get(self, build)
 
-    def run(self, x_norm: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+    def run(self, x_norm: torch.Tensor, residual: torch.Tensor, **kw) -> torch.Tensor:
         pk = self.packed()
         h = ops.gemm(x_norm, pk["w1"], bias=pk["b1"], geglu=True)
-        return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=residual)
+        return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=residual, **kw)
+
+    def folded(self, gamma: torch.Tensor, beta: torch.Tensor):
+        """GEGLU projection with the preceding LayerNorm (gamma, beta) folded in: (w1', colsum, b1'), value / gate rows
+        interleaved like packed()['w1']."""
+        wg, colsum, bias = fold_layer_norm(self.net[0].proj.weight, self.net[0].proj.bias, gamma, beta)
+        w1, b1 = ops.interleave_geglu(wg, bias)
+        cs1, _ = ops.interleave_geglu(colsum[:, None], None)
+        return w1, cs1.reshape(-1).contiguous(), b1
+
+    def run_folded(self, x: torch.Tensor, stats, fold, residual: torch.Tensor, eps: float = 1e-5, **kw) -> torch.Tensor:
+        """x is the UN-normalised input; `stats` its RowStats from the producer's epilogue; fold = self.folded(...)."""
+        pk = self.packed()
+        w1, cs1, b1 = fold
+        h = ops.gemm(x, w1, bias=b1, geglu=True, ln=ops.LNFold(stats, cs1, eps))
+        return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=residual, **kw)
 
 
 class Attention(nn.Module):
@@ -121,13 +170,19 @@ class ResnetBlock(nn.Module):
         pk = self.packed()
         nf, h, w, _ = x.shape
         cout = self.out_channels
-        hn = ops.group_norm(x, pk["g1"], pk["b1"], self.groups, self.eps, True, x2=skip)
+        # GroupNorm statistics come from the epilogue of whatever produced x / skip / hc (ColStats tags); a source without a
+        # tag (conv_in + pose, x + pose feature) makes that GroupNorm run its own statistics pass
+        emit = FUSE_NORMS and ops.conv_col_stats_ok(nf, h, w) and cout % 32 == 0
+        hn = ops.group_norm(x, pk["g1"], pk["b1"], self.groups, self.eps, True, x2=skip, stats=_cs(x),
+                            stats2=_cs(skip) if skip is not None else None)
         if self.time_emb_proj is not None:
-            bias1 = ops.gemm(ctx.temb_act, pk["wt"], bias=pk["bt"], out_f32=True)            # [B, cout] fp32
-            hc = ops.conv3x3(hn, pk["w1"], cout, bias=bias1, bias_group_rows=ctx.F * h * w)
+            tb = ctx.temb_bias.get(id(self)) if ctx.temb_bias is not None else None
+            bias1 = tb if tb is not None else ops.gemm(ctx.temb_act, pk["wt"], bias=pk["bt"], out_f32=True)   # [B, cout]
+            hc = ops.conv3x3(hn, pk["w1"], cout, bias=bias1, bias_group_rows=ctx.F * h * w, col_stats=emit)
         else:
-            hc = ops.conv3x3(hn, pk["w1"], cout, bias=pk["cb1"])
-        hn2 = ops.group_norm(hc, pk["g2"], pk["b2"], self.groups, self.eps, True)
+            hc = ops.conv3x3(hn, pk["w1"], cout, bias=pk["cb1"], col_stats=emit)
+        hc, cs_hc = hc if emit else (hc, None)
+        hn2 = ops.group_norm(hc, pk["g2"], pk["b2"], self.groups, self.eps, True, stats=cs_hc)
         if self.conv_shortcut is not None:
             c1 = x.shape[-1]
             a = x.view(-1, c1)
@@ -136,7 +191,8 @@ class ResnetBlock(nn.Module):
         else:
             assert skip is None
             res = x
-        return ops.conv3x3(hn2, pk["w2"], cout, bias=pk["cb2"], residual=res)
+        out = ops.conv3x3(hn2, pk["w2"], cout, bias=pk["cb2"], residual=res, col_stats=emit)
+        return _tag(*out) if emit else out
 
 
 class Downsample(nn.Module):
@@ -149,7 +205,10 @@ class Downsample(nn.Module):
 
     def run(self, x):
         pk = self._pk.get(self, lambda: dict(w=ops.pack_conv3x3_weight(self.conv.weight.detach()), b=f32(self.conv.bias)))
-        return ops.conv3x3(x, pk["w"], self.conv.out_channels, bias=pk["b"], stride=2)
+        nf, h, w, _ = x.shape
+        emit = FUSE_NORMS and ops.conv_col_stats_ok(nf, h // 2, w // 2) and self.conv.out_channels % 32 == 0
+        out = ops.conv3x3(x, pk["w"], self.conv.out_channels, bias=pk["b"], stride=2, col_stats=emit)
+        return _tag(*out) if emit else out
 
 
 class Upsample(nn.Module):
@@ -162,7 +221,10 @@ class Upsample(nn.Module):
 
     def run(self, x):
         pk = self._pk.get(self, lambda: dict(w=ops.pack_conv3x3_weight(self.conv.weight.detach()), b=f32(self.conv.bias)))
-        return ops.conv3x3(ops.upsample2x(x), pk["w"], self.conv.out_channels, bias=pk["b"])
+        nf, h, w, _ = x.shape
+        emit = FUSE_NORMS and ops.conv_col_stats_ok(nf, 2 * h, 2 * w) and self.conv.out_channels % 32 == 0
+        out = ops.conv3x3(ops.upsample2x(x), pk["w"], self.conv.out_channels, bias=pk["b"], col_stats=emit)
+        return _tag(*out) if emit else out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -207,6 +269,18 @@ class BasicTransformerBlock(nn.Module):
             if self.attn2 is not None:
                 d.update(wv2=f16(self.attn2.to_v.weight), wo2=f16(self.attn2.to_out[0].weight),
                          bo2o=(f32(self.attn2.to_out[0].bias) + f32(self.attn1.to_out[0].bias)).contiguous())
+            # norm1 folded into the q/k/v projection, norm3 into the GEGLU projection (fold_layer_norm); the padded head
+            # rows stay zero (zero weight rows -> zero colsum and bias)
+            qkv_w = torch.cat([self.attn1.to_q.weight, self.attn1.to_k.weight, self.attn1.to_v.weight], 0)
+            wg, cs, bias = fold_layer_norm(qkv_w, None, self.norm1.weight, self.norm1.bias)
+            inner = self.heads * self.dim_head
+            d["wqkv_g"] = torch.cat([ops.pad_head_rows(wg[i * inner:(i + 1) * inner], self.heads, dpad) for i in range(3)],
+                                    0).contiguous()
+            pad1 = lambda v: ops.pad_head_rows(v[:, None], self.heads, dpad).reshape(-1)    # noqa: E731
+            d["cs_qkv"] = torch.cat([pad1(cs[i * inner:(i + 1) * inner]) for i in range(3)]).contiguous()
+            d["b_qkv"] = torch.cat([pad1(bias[i * inner:(i + 1) * inner]) for i in range(3)]).contiguous()
+            d["ff_fold"] = self.ff.folded(self.norm3.weight, self.norm3.bias)
+            d["eps1"], d["eps3"] = self.norm1.eps, self.norm3.eps
             return d
         return self._pk.get(self, build)
 
@@ -254,15 +328,24 @@ class BasicTransformerBlock(nn.Module):
         if self._ref_mode == "read" and len(self.bank) > 0:
             self._bank_projection(pk, self.bank[0].shape[1])
 
-    def run(self, t0: torch.Tensor, n_frames: int, tokens: int, ctx: RunCtx) -> torch.Tensor:
-        """t0: [n_frames*tokens, dim] fp16."""
+    def fused(self) -> bool:
+        """LayerNorm folding is used unless the block has to materialise norm1(x) for the bank (ReferenceNet write pass)."""
+        return FUSE_NORMS and self._ref_mode != "write"
+
+    def run(self, t0: torch.Tensor, n_frames: int, tokens: int, ctx: RunCtx, t0_stats=None, out_kw=None) -> torch.Tensor:
+        """t0: [n_frames*tokens, dim] fp16. t0_stats: RowStats of t0 from its producer's epilogue (required when fused()).
+        out_kw: extra ops.gemm arguments for the block's LAST GEMM (the caller may ask for statistics of the output)."""
         pk = self.packed()
         dpad, heads, d = pk["dpad"], self.heads, self.dim_head
         hp = heads * dpad
-        n1 = ops.layer_norm(t0, pk["g1"], pk["b1"])
-        if self._ref_mode == "write":
-            self.bank.append(n1.view(n_frames, tokens, self.dim).clone())
-        qkv = ops.gemm(n1, pk["wqkv"])
+        fused = self.fused() and t0_stats is not None
+        if fused:
+            qkv = ops.gemm(t0, pk["wqkv_g"], bias=pk["b_qkv"], ln=ops.LNFold(t0_stats, pk["cs_qkv"], pk["eps1"]))
+        else:
+            n1 = ops.layer_norm(t0, pk["g1"], pk["b1"], pk["eps1"])
+            if self._ref_mode == "write":
+                self.bank.append(n1.view(n_frames, tokens, self.dim).clone())
+            qkv = ops.gemm(n1, pk["wqkv"])
         q, k, v = qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:]
         kw = {}
         if self._ref_mode == "read" and len(self.bank) > 0 and ctx.ref_branch != "uncond":
@@ -289,9 +372,14 @@ class BasicTransformerBlock(nn.Module):
                           first_bank_frame=0, frames_per_bank=ctx.F)
         a = ops.attention(q, k, v, n_frames, tokens, heads, d, dpad, **kw)
         bias, grouped = self._attn_out_bias(pk, ctx)
-        t1 = ops.gemm(a, pk["wo"], bias=bias, residual=t0, bias_group_rows=(ctx.F * tokens if grouped else 0))
-        n3 = ops.layer_norm(t1, pk["g3"], pk["b3"])
-        return self.ff.run(n3, t1)
+        gr = ctx.F * tokens if grouped else 0
+        out_kw = out_kw or {}
+        if fused:
+            t1, st1 = ops.gemm(a, pk["wo"], bias=bias, residual=t0, bias_group_rows=gr, row_stats=True)
+            return self.ff.run_folded(t1, st1, pk["ff_fold"], t1, pk["eps3"], **out_kw)
+        t1 = ops.gemm(a, pk["wo"], bias=bias, residual=t0, bias_group_rows=gr)
+        n3 = ops.layer_norm(t1, pk["g3"], pk["b3"], pk["eps3"])
+        return self.ff.run(n3, t1, **out_kw)
 
 
 class TemporalBasicTransformerBlock(BasicTransformerBlock):
@@ -325,10 +413,17 @@ class SpatialTransformer(nn.Module):
     def run(self, x: torch.Tensor, ctx: RunCtx) -> torch.Tensor:
         pk = self.packed()
         nf, h, w, c = x.shape
-        hn = ops.group_norm(x, pk["g"], pk["b"], self.groups, 1e-6, False)
-        t0 = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"])
-        t = self.transformer_blocks[0].run(t0, nf, h * w, ctx)
-        out = ops.gemm(t, pk["wo"], bias=pk["bo"], residual=x.view(-1, c))
+        blk = self.transformer_blocks[0]
+        hn = ops.group_norm(x, pk["g"], pk["b"], self.groups, 1e-6, False, stats=_cs(x))
+        if blk.fused():
+            t0, st0 = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"], row_stats=True)
+        else:
+            t0, st0 = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"]), None
+        t = blk.run(t0, nf, h * w, ctx, t0_stats=st0)
+        emit = ctx.emit_stats and (h * w) % 32 == 0 and c % 32 == 0
+        out = ops.gemm(t, pk["wo"], bias=pk["bo"], residual=x.view(-1, c), col_stats=emit)
+        if emit:
+            return _tag(out[0].view(nf, h, w, c), out[1])
         return out.view(nf, h, w, c)
 
 
@@ -399,8 +494,35 @@ class TemporalTransformer3DModel(nn.Module):
                     b=f32(blk.norms[i].bias),
                     # the reference adds the (fp16) buffer to the LayerNorm output: keep its rounding
                     pe=at.pos_encoder.pe[0].detach().to(torch.float16).to(torch.float32).contiguous()))
+                # norms[i] folded into the q/k/v projection; beta and the positional encoding become a per-frame bias table
+                qkv_w = torch.cat([at.to_q.weight, at.to_k.weight, at.to_v.weight], 0)
+                wg, cs, _ = fold_layer_norm(qkv_w, None, blk.norms[i].weight, blk.norms[i].bias)
+                d["attn"][i].update(wqkv_g=wg, cs=cs, eps=blk.norms[i].eps)
+            d["ff_fold"] = blk.ff.folded(blk.ff_norm.weight, blk.ff_norm.bias)
+            d["eps_f"] = blk.ff_norm.eps
+            d["pe_bias"] = {}
             return d
         return self._pk.get(self, build)
+
+    @staticmethod
+    def _pe_bias(pk, i, B, F):
+        """Bias table of the folded q/k/v projection: row b * F + f = (beta + pe[f]) . Wqkv^T  (LN(m) + pe[f] is what the
+        reference projects, motion_module.py:365-366). Built once per (batch, window length)."""
+        key = (i, B, F)
+        tab = pk["pe_bias"].get(key)
+        if tab is None:
+            a = pk["attn"][i]
+            t = (a["b"][None, :] + a["pe"][:F]) @ a["wqkv"].to(torch.float32).t()         # [F, 3C]
+            tab = t.repeat(B, 1).contiguous()
+            pk["pe_bias"][key] = tab
+        return tab
+
+    def prepare(self, batch: int, frames: int):
+        """Per-geometry precompute outside any CUDA-graph capture (torch math: a 32 x C by C x 3C matmul per attention)."""
+        if FUSE_NORMS:
+            pk = self.packed()
+            for i in range(2):
+                self._pe_bias(pk, i, batch, frames)
 
     def run(self, x: torch.Tensor, ctx: RunCtx) -> torch.Tensor:
         pk = self.packed()
@@ -408,17 +530,30 @@ class TemporalTransformer3DModel(nn.Module):
         n_tok = h * w
         if ctx.F > self.max_len:
             raise ValueError(f"window of {ctx.F} frames exceeds temporal_position_encoding_max_len={self.max_len}")
-        hn = ops.group_norm(x, pk["g"], pk["b"], self.groups, 1e-6, False)
-        m = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"])
-        for i in range(2):
-            a = pk["attn"][i]
-            n = ops.layer_norm(m, a["g"], a["b"], pe=a["pe"], rows_per_pe=n_tok, pe_period=ctx.F)
-            qkv = ops.gemm(n, a["wqkv"])
-            o = ops.temporal_attention(qkv, ctx.B, ctx.F, n_tok, c, self.heads)
-            m = ops.gemm(o, a["wo"], bias=a["bo"], residual=m)
-        n = ops.layer_norm(m, pk["gf"], pk["bf"])
-        m = self.transformer_blocks[0].ff.run(n, m)
-        out = ops.gemm(m, pk["wo"], bias=pk["bo"], residual=x.view(-1, c))
+        hn = ops.group_norm(x, pk["g"], pk["b"], self.groups, 1e-6, False, stats=_cs(x))
+        emit = ctx.emit_stats and n_tok % 32 == 0 and c % 32 == 0
+        if FUSE_NORMS:
+            m, st = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"], row_stats=True)
+            for i in range(2):
+                a = pk["attn"][i]
+                qkv = ops.gemm(m, a["wqkv_g"], bias=self._pe_bias(pk, i, ctx.B, ctx.F), bias_group_rows=n_tok,
+                               ln=ops.LNFold(st, a["cs"], a["eps"]))
+                o = ops.temporal_attention(qkv, ctx.B, ctx.F, n_tok, c, self.heads)
+                m, st = ops.gemm(o, a["wo"], bias=a["bo"], residual=m, row_stats=True)
+            m = self.transformer_blocks[0].ff.run_folded(m, st, pk["ff_fold"], m, pk["eps_f"])
+        else:
+            m = ops.gemm(hn.view(-1, c), pk["wi"], bias=pk["bi"])
+            for i in range(2):
+                a = pk["attn"][i]
+                n = ops.layer_norm(m, a["g"], a["b"], a["eps"], pe=a["pe"], rows_per_pe=n_tok, pe_period=ctx.F)
+                qkv = ops.gemm(n, a["wqkv"])
+                o = ops.temporal_attention(qkv, ctx.B, ctx.F, n_tok, c, self.heads)
+                m = ops.gemm(o, a["wo"], bias=a["bo"], residual=m)
+            n = ops.layer_norm(m, pk["gf"], pk["bf"], pk["eps_f"])
+            m = self.transformer_blocks[0].ff.run(n, m)
+        out = ops.gemm(m, pk["wo"], bias=pk["bo"], residual=x.view(-1, c), col_stats=emit)
+        if emit:
+            return _tag(out[0].view(nf, h, w, c), out[1])
         return out.view(nf, h, w, c)
 
 

@@ -144,7 +144,7 @@ class PoseGuider(ModelBase):
             raise RuntimeError("aniportrait_b200.PoseGuider runs in fp16 (`.to(device, torch.float16)`): no fp32 / library path")
         pk = self.packed()
         frames, cin, H, W = x.shape
-        ctx = RunCtx(1, frames, None, None)
+        ctx = RunCtx(1, frames, None, None, emit_stats=False)     # no GroupNorm consumes the transformer outputs here
         x = ops.ncfhw_to_nhwc(x.to(torch.float16).contiguous().view(frames, cin, 1, H, W), 8)      # [frames, H, W, 8]
         for d in pk["stem"]:
             x = self._conv_bn_relu(x, d)

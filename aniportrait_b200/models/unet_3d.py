@@ -200,8 +200,23 @@ class UNet3DConditionModel(ModelBase):
             wo = ops.pack_conv3x3_weight(self.conv_out.weight.detach())
             bo = torch.zeros(wo.shape[0], dtype=torch.float32, device=wo.device)
             bo[:cout] = f32(self.conv_out.bias)
+            # every resnet's time-embedding projection in ONE GEMM per call (reference resnet.py:226-230 runs 22 small
+            # Linears): rows of all time_emb_proj weights concatenated; resnet r reads columns [off_r, off_r + cout_r)
+            from .blocks import ResnetBlock
+            res = [m for m in self.modules() if isinstance(m, ResnetBlock) and m.time_emb_proj is not None]
+            temb = None
+            if res:
+                pks = [m.packed() for m in res]
+                offs, o = [], 0
+                for m in res:
+                    offs.append(o)
+                    o += m.out_channels
+                if o % 32 == 0:
+                    temb = dict(w=torch.cat([q["wt"] for q in pks], 0).contiguous(),
+                                b=torch.cat([q["bt"] for q in pks], 0).contiguous(),
+                                slices=[(id(m), off, m.out_channels) for m, off in zip(res, offs)])
             return dict(wi=ops.pack_conv3x3_weight(self.conv_in.weight.detach()), bi=f32(self.conv_in.bias),
-                        gn=f32(self.conv_norm_out.weight), bn=f32(self.conv_norm_out.bias), wo=wo, bo=bo)
+                        gn=f32(self.conv_norm_out.weight), bn=f32(self.conv_norm_out.bias), wo=wo, bo=bo, temb=temb)
         return self._pk.get(self, build)
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -223,7 +238,12 @@ class UNet3DConditionModel(ModelBase):
         t_emb = ops.timestep_embedding(t.contiguous(), self.conv_in.out_channels)
         emb = self.time_embedding.run(t_emb)
         ehs = encoder_hidden_states.to(torch.float16).contiguous() if encoder_hidden_states is not None else None
-        ctx = RunCtx(batch, frames, ops.silu(emb), ehs, ehs_key=ehs_key, ref_branch=ref_branch)   # see RunCtx
+        temb_act = ops.silu(emb)
+        temb_bias = None
+        if pk["temb"] is not None:
+            tb = ops.gemm(temb_act, pk["temb"]["w"], bias=pk["temb"]["b"], out_f32=True)            # [B, sum of couts] fp32
+            temb_bias = {rid: tb[:, off:off + n] for rid, off, n in pk["temb"]["slices"]}
+        ctx = RunCtx(batch, frames, temb_act, ehs, ehs_key=ehs_key, ref_branch=ref_branch, temb_bias=temb_bias)
 
         def add_pose(x, k):
             if pose_nhwc is None:
@@ -248,7 +268,8 @@ class UNet3DConditionModel(ModelBase):
                 x = blk.layer(j, x, ctx, skip=skips.pop())
             if blk.upsamplers is not None:
                 x = blk.upsamplers[0].run(x)
-        hn = ops.group_norm(x, pk["gn"], pk["bn"], self.groups, self.eps, True)
+        from .blocks import _cs
+        hn = ops.group_norm(x, pk["gn"], pk["bn"], self.groups, self.eps, True, stats=_cs(x))
         return ops.conv3x3(hn, pk["wo"], self.conv_out.out_channels, bias=pk["bo"])
 
     def prepare_reference(self, batch: int, frames: int, encoder_hidden_states, ehs_key=None, ref_branch=None):
@@ -260,9 +281,12 @@ class UNet3DConditionModel(ModelBase):
         if ehs_key is None:
             raise ValueError("prepare_reference needs an explicit ehs_key (the identity of this video's conditioning)")
         ctx = RunCtx(batch, frames, None, ehs, ehs_key=ehs_key, ref_branch=ref_branch)
+        from .blocks import TemporalTransformer3DModel
         for m in self.modules():
             if isinstance(m, BasicTransformerBlock):
                 m.prepare(ctx)
+            elif isinstance(m, TemporalTransformer3DModel):
+                m.prepare(batch, frames)       # positional-encoding bias tables of the folded q/k/v projections
 
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, pose_cond_fea=None,
                 attention_mask=None, down_block_additional_residuals=None, mid_block_additional_residual=None,

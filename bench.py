@@ -220,6 +220,10 @@ def kernel_rooflines(device, peaks):
     hp = heads * dpad
     qkv = torch.randn(fr * n, 3 * hp, device=device, dtype=torch.float16)
     bank = torch.randn(n, 2 * hp, device=device, dtype=torch.float16)
+    # the head padding d..dpad is ZERO in real use (zero rows of the packed projection weights); the kernel multiplies the
+    # first 48 of the 64 columns
+    qkv.view(fr * n, 3 * heads, dpad)[:, :, d:] = 0
+    bank.view(n, 2 * heads, dpad)[:, :, d:] = 0
     o = torch.empty(fr * n, heads * d, device=device, dtype=torch.float16)
     ms = time_it(lambda: ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], fr, n, heads, d, dpad,
                                        bank_k=bank[:, :hp], bank_v=bank[:, hp:], bank_tokens=n, n_banks=1,
@@ -316,7 +320,7 @@ def run_strong_c4(pipe, device, rank, world, local_rank, base_on_rank0=True):
         return best, ph, pipe.last_latents.float().cpu()
 
     barrier()
-    ms, ph, lat_sharded = timed(mode, 2)
+    ms, ph, lat_sharded = timed(mode, 2 if world > 1 else 1)
     # per-rank split: device ms inside the unit graphs = denoise - all-reduce (which includes waiting for slower ranks)
     mine = torch.tensor([ms, ph["denoise_ms"], ph.get("all_reduce_ms", 0.0), ph.get("bank_broadcast_ms", 0.0),
                          ph.get("all_gather_ms", 0.0), ph["reference_ms"], ph["decode_ms"], float(ph["units_this_rank"])],
@@ -554,6 +558,7 @@ def cpu_baseline_sample(threads=None):
     from oracle import functional as OF
     threads = threads or min(os.cpu_count() or 1, 32)   # torch CPU conv/GEMM stops scaling (and oversubscribes) beyond ~32
     torch.set_num_threads(threads)
+    OF.USE_SDPA = True      # time the library attention the reference itself calls (AttnProcessor2_0 -> SDPA), see oracle
     t_build = time.perf_counter()
     sd3 = randomize_state_dict(meta_state_dict(lambda: UNet3DConditionModel(
         cross_attention_dim=768, use_inflated_groupnorm=True, unet_use_cross_frame_attention=False,

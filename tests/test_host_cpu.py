@@ -14,6 +14,11 @@ sys.path.insert(0, ROOT)
 from oracle import functional as OF  # noqa: E402
 
 
+def rel_l2(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
 def test_library_exports_every_declared_symbol():
     from aniportrait_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):
@@ -316,3 +321,73 @@ def test_pipeline_rejects_schedulers_the_fused_step_cannot_reproduce():
         config = dict(prediction_type="epsilon")
     with pytest.raises(NotImplementedError):
         P(NoAlphas())._scheduler_update_rule()
+
+
+def test_layernorm_folding_algebra():
+    """Host side of the LayerNorm folding (aniportrait_b200/models/blocks.py::fold_layer_norm, FeedForward.folded, the motion
+    module's positional-encoding bias table) evaluated with plain torch: rstd (x W'^T - mean colsum) + bias' == LN(x) W^T + b."""
+    import torch.nn.functional as F
+    from aniportrait_b200 import ops
+    from aniportrait_b200.models.blocks import FeedForward, TemporalTransformer3DModel, fold_layer_norm
+    g = torch.Generator().manual_seed(0)
+    M, C, N = 50, 64, 96
+    x = torch.randn(M, C, generator=g) + 0.4
+    w, b = torch.randn(N, C, generator=g) * C ** -0.5, torch.randn(N, generator=g) * 0.1
+    gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    wg, cs, bias = fold_layer_norm(w, b, gamma, beta)
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    got = rstd * (x @ wg.float().t() - mean * cs[None]) + bias[None]
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b
+    assert rel_l2(got, ref) < 2e-3          # W' is rounded to fp16
+    # GEGLU: the folded, interleaved projection pairs value / gate columns like the kernel's epilogue expects
+    ff = FeedForward(C)
+    w1, cs1, b1 = ff.folded(gamma, beta)
+    acc = rstd * (x @ w1.float().t() - mean * cs1[None]) + b1[None]                      # [M, 8C] interleaved 16 | 16
+    a = acc.view(M, -1, 2, 16)
+    got = (a[:, :, 0] * F.gelu(a[:, :, 1])).reshape(M, -1)
+    h, gate = (F.layer_norm(x, (C,), gamma, beta, 1e-5) @ ff.net[0].proj.weight.t() + ff.net[0].proj.bias).chunk(2, -1)
+    assert rel_l2(got, h * F.gelu(gate)) < 2e-3
+    # motion module: LN(m) + pe[f] projected by Wqkv == folded GEMM + per-frame bias table
+    mm = TemporalTransformer3DModel(C, heads=8, max_len=32, groups=32)
+    for p in mm.parameters():
+        torch.nn.init.normal_(p, std=0.3)
+    pk = mm.packed()
+    B, Fr, n_tok = 2, 5, 3
+    m = torch.randn(B * Fr * n_tok, C, generator=g)
+    a0 = pk["attn"][0]
+    tab = mm._pe_bias(pk, 0, B, Fr)                                                        # [B*F, 3C]
+    mean, rstd = m.mean(1, keepdim=True), (m.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    rows = torch.arange(B * Fr * n_tok) // n_tok
+    got = rstd * (m @ a0["wqkv_g"].float().t() - mean * a0["cs"][None]) + tab[rows]
+    frame = rows % Fr
+    n = F.layer_norm(m, (C,), a0["g"], a0["b"], 1e-5) + a0["pe"][frame]
+    assert rel_l2(got, n @ a0["wqkv"].float().t()) < 2e-3
+
+
+def test_vae_quant_conv_folding_algebra():
+    """AutoencoderKL: quant_conv folded into encoder.conv_out, post_quant_conv folded into decoder.conv_in over a
+    constant-one channel (aniportrait_b200/models/vae.py) == the two-convolution chains, borders included."""
+    import torch.nn.functional as F
+    from aniportrait_b200.models.vae import AutoencoderKL
+    vae = AutoencoderKL(block_out_channels=(64, 64, 64, 64))
+    for p in vae.parameters():
+        torch.nn.init.normal_(p, std=0.2)
+    g = torch.Generator().manual_seed(1)
+    # encoder tail
+    pk = vae.encoder._packed(vae.quant_conv)
+    wo, bo = pk["conv_out"]                                  # [32 (padded), 9 * 64] tap-major / channel-minor
+    w_f = wo[:8].float().view(8, 3, 3, 64).permute(0, 3, 1, 2)
+    x = torch.randn(2, 64, 6, 5, generator=g)
+    ref = vae.quant_conv(vae.encoder.conv_out(x))
+    got = F.conv2d(x, w_f, bo[:8], padding=1)
+    assert rel_l2(got, ref) < 2e-3
+    # decoder head
+    pk = vae.decoder._packed(vae.post_quant_conv)
+    wi, bi = pk["conv_in"]                                   # [64, 9 * 64]: channels 0..3 latent, 4 the ones channel
+    w_f = wi.float().view(-1, 3, 3, 64).permute(0, 3, 1, 2)[:, :5]
+    z = torch.randn(2, 4, 6, 5, generator=g)
+    ref = vae.decoder.conv_in(vae.post_quant_conv(z))
+    z1 = torch.cat([z, torch.ones(2, 1, 6, 5)], 1)
+    got = F.conv2d(z1, w_f, bi[:64], padding=1)
+    assert rel_l2(got, ref) < 2e-3

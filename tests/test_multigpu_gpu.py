@@ -1,6 +1,7 @@
 """N>1 path on real GPUs (needs >= 2 visible devices, otherwise skipped): two NCCL ranks shard the frame windows of one
-video (dist_mode="windows": ReferenceNet banks broadcast from rank 0, one fp32 sum all-reduce of the accumulated noise
-prediction per step, decoded frames all-gathered) and must reproduce the single-process result; dist_mode="clips" (the
+video (dist_mode="windows": cached CUDA-graph session per rank, ReferenceNet banks broadcast from rank 0 as ONE flat buffer,
+one fp32 sum all-reduce of the accumulated noise prediction per step, decoded frames all-gathered) and must reproduce the
+single-process result; dist_mode="clips" (the
 weak-scaling mode bench.py uses for N>1) must leave every rank with its own, locally computed video."""
 import os
 import sys
@@ -32,8 +33,13 @@ def _worker(rank, world, port, q):
     args = (ref_image, poses, ref_pose, P["size"], P["size"], L, 3, P["guidance"])
     single = pipe(*args, latents=lat0.clone()).videos if rank == 0 else None
     single_lat = pipe.last_latents.float().cpu() if rank == 0 else None
-    sharded = pipe(*args, latents=lat0.clone(), dist_mode="windows").videos
+    sharded = pipe(*args, latents=lat0.clone(), dist_mode="windows").videos      # builds + captures the sharded session
     sharded_lat = pipe.last_latents.float().cpu()
+    again = pipe(*args, latents=lat0.clone(), dist_mode="windows").videos        # pure replay: rank-0 write graph, ONE flat
+    assert torch.equal(again, sharded)                                           # bank broadcast, read graph, unit graphs
+    assert torch.equal(pipe.last_latents.float().cpu(), sharded_lat)
+    pipe.collect_timings()
+    assert pipe.timings.get("bank_broadcast_ms", 0.0) > 0.0 and pipe.timings.get("all_reduce_ms", 0.0) > 0.0
     pipe(*args, latents=lat0.clone(), dist_mode="window_branches")        # (window, CFG branch) units: 4 units on 2 ranks
     branch_lat = pipe.last_latents.float().cpu()
     # clips mode: every rank runs its own clip end to end (rank-dependent noise), no data-path collective

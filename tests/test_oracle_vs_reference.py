@@ -50,7 +50,13 @@ def test_unet3d_plain_forward(nets):
     with torch.no_grad():
         ref = unet3d(x, torch.tensor(500), encoder_hidden_states=ehs, pose_cond_fea=pose, return_dict=False)[0]
         ours = OF.unet3d_forward(sd3, x, 500, ehs, pose, banks=None, cfg=False, c=CFG_SMALL)
+        OF.USE_SDPA = True        # the variant bench.py's CPU-baseline leg times (library SDPA, as the reference calls it)
+        try:
+            ours_sdpa = OF.unet3d_forward(sd3, x, 500, ehs, pose, banks=None, cfg=False, c=CFG_SMALL)
+        finally:
+            OF.USE_SDPA = False
     assert rel_l2(ours, ref) < 1e-5
+    assert rel_l2(ours_sdpa, ref) < 1e-5
 
 
 def test_reference_attention_read_write(nets):
