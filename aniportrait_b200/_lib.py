@@ -79,8 +79,7 @@ LL = c_longlong
 class EpilogueExt(ctypes.Structure):
     """ap_epilogue_ext of include/aniportrait_b200.h."""
     _fields_ = [("row_stat_out", c_void_p), ("row_stat_ld", c_longlong), ("col_stat_out", c_void_p),
-                ("col_stat_ld", c_longlong), ("ln_stat", c_void_p), ("ln_parts", c_int), ("ln_stat_ld", c_longlong),
-                ("ln_colsum", c_void_p), ("ln_eps", c_float), ("bias_ld", c_longlong)]
+                ("col_stat_ld", c_longlong), ("ln_rstd", c_void_p), ("bias_ld", c_longlong)]
 
 
 def ext_ptr(ext):

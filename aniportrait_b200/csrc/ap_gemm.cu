@@ -69,13 +69,11 @@ struct GemmParams {
   float2* col_stat_out;    // GroupNorm of the NEXT op: {sum, sumsq} per output column over the 32 rows of the warp's TMEM lane
                            // quarter: [4 * m_tile + quarter][col_stat_ld]
   long long col_stat_ld;
-  // Consumer side: this GEMM's A operand is x, its weights carry the LayerNorm scale (W' = W diag(gamma)); the epilogue
-  // turns acc = x.W'^T into LN(x).W^T = rstd (acc - mean colsum(W')) + (beta.W^T + b) [the last term arrives as `bias`].
-  const float2* ln_stat;   // [ln_parts][ln_stat_ld] row partials written by the producer of x
-  int ln_parts;
-  long long ln_stat_ld;
-  const float* ln_colsum;  // [N] fp32: sum_k W'[n, k]
-  float ln_inv_k, ln_eps;
+  // Consumer side (LayerNorm folded into this GEMM): A = [x | -mean (hi, lo, hi)], W = [W diag(gamma) | colsum (hi, hi, lo)],
+  // so the accumulator already holds x.W'^T - mean colsum(W') (the mean term rides on one extra k-block of the tensor
+  // core; the two-source A path existed for the skip concat); the epilogue only scales by the row's rstd:
+  //   out = rstd * acc + (beta.W^T + b)   [the last term arrives as `bias`]: one FMA where the bias add used to be.
+  const float* ln_rstd;    // [M] fp32, written by ln_finalize_kernel from the producer's row partials
 };
 
 // NACC = 2 ("wide" tile, cta_group::2 only): one staged A tile feeds TWO N = BN accumulators (two adjacent BN-wide weight
@@ -336,6 +334,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
       const int sw = (lane >> 1) & 3;                       // 64B-swizzle XOR term of this thread's row
       const int r0 = lane_group * 32;
+      // LayerNorm-folding consumers: rstd of this thread's row in the NEXT tile
+      float ln_next = 1.f;
+      auto ln_prefetch = [&](int tile_) {
+        if (tile_ >= num_tiles) return;
+        const long long mm = (long long)((tile_ / n_groups) * CG + (int)cta_rank) * Cfg::BM + r0 + lane;   // A_GEMM rows
+        ln_next = mm < p.M ? __ldg(p.ln_rstd + mm) : 1.f;
+      };
+      if (p.ln_rstd != nullptr) ln_prefetch(first_tile);
       uint32_t it = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
         const int m_tile = (tile / n_groups) * CG + (int)cta_rank;
@@ -366,18 +372,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         }
         const float* bias_row = nullptr;
         if (p.bias != nullptr) bias_row = p.bias + (row_ok ? (m / p.bias_group_rows) : 0) * p.bias_ld;
-        // LayerNorm folding (consumer): row statistics from the producer's partials, summed in a fixed order
-        float ln_mean = 0.f, ln_rstd = 1.f;
-        if (p.ln_stat != nullptr) {
-          float S = 0.f, Q = 0.f;
-          if (row_ok)
-            for (int i = 0; i < p.ln_parts; ++i) {
-              const float2 t = __ldg(p.ln_stat + (long long)i * p.ln_stat_ld + m);
-              S += t.x;
-              Q += t.y;
-            }
-          ln_mean = S * p.ln_inv_k;
-          ln_rstd = rsqrtf(fmaxf(Q * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+        // LayerNorm folding (consumer): the row's rstd, requested one tile ago (with K = 320 the epilogue is the critical
+        // path: a load issued at the top of the tile is fully exposed)
+        float ln_a = 1.f;
+        if (p.ln_rstd != nullptr) {
+          ln_a = ln_next;
+          ln_prefetch(tile + tile_stride);
         }
         float rs_s = 0.f, rs_q = 0.f;   // producer: this warp's share of the row's {sum, sumsq}
         const bool want_stats = (EPI == EPI_LINEAR) && (p.row_stat_out != nullptr || p.col_stat_out != nullptr);
@@ -430,22 +430,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
                   bg[4 * j] = g.x; bg[4 * j + 1] = g.y; bg[4 * j + 2] = g.z; bg[4 * j + 3] = g.w;
                 }
               }
-              if (p.ln_stat != nullptr) {   // acc -> rstd (acc - mean colsum) for the value and the gate columns
-                const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + acol + h * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 cs = __ldg(c4 + j);
-                  const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
-#pragma unroll
-                  for (int t = 0; t < 4; ++t)
-                    r[h * 32 + 4 * j + t] = __float_as_uint(
-                        ln_rstd * (__uint_as_float(r[h * 32 + 4 * j + t]) - ln_mean * cc[t]));
-                }
-              }
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                v[h * 16 + j] = (__uint_as_float(r[h * 32 + j]) + bv[j]) *
-                                gelu_erf(__uint_as_float(r[h * 32 + 16 + j]) + bg[j]);
+                v[h * 16 + j] = fmaf(__uint_as_float(r[h * 32 + j]), ln_a, bv[j]) *
+                                gelu_erf(fmaf(__uint_as_float(r[h * 32 + 16 + j]), ln_a, bg[j]));
             }
           } else {
             uint32_t r[32];
@@ -453,18 +441,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.ln_stat != nullptr) {
-              const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + acol);
+            if (p.ln_rstd != nullptr) {   // v = rstd * acc + bias (the folded beta.W^T + b: always present)
+              const float4* b4 = reinterpret_cast<const float4*>(bias_row + acol);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 cs = __ldg(c4 + j);
-                v[4 * j + 0] = ln_rstd * (v[4 * j + 0] - ln_mean * cs.x);
-                v[4 * j + 1] = ln_rstd * (v[4 * j + 1] - ln_mean * cs.y);
-                v[4 * j + 2] = ln_rstd * (v[4 * j + 2] - ln_mean * cs.z);
-                v[4 * j + 3] = ln_rstd * (v[4 * j + 3] - ln_mean * cs.w);
+                const float4 b = __ldg(b4 + j);
+                v[4 * j + 0] = fmaf(v[4 * j + 0], ln_a, b.x);
+                v[4 * j + 1] = fmaf(v[4 * j + 1], ln_a, b.y);
+                v[4 * j + 2] = fmaf(v[4 * j + 2], ln_a, b.z);
+                v[4 * j + 3] = fmaf(v[4 * j + 3], ln_a, b.w);
               }
-            }
-            if (bias_row != nullptr) {
+            } else if (bias_row != nullptr) {
               const float4* b4 = reinterpret_cast<const float4*>(bias_row + acol);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -820,7 +807,7 @@ static int apply_ext(GemmParams& p, const ap_epilogue_ext* ext, int epi, long lo
   p.bias_ld = p.N;
   if (ext == nullptr) return AP_OK;
   if (ext->bias_ld > 0) p.bias_ld = ext->bias_ld;
-  const bool any = ext->row_stat_out || ext->col_stat_out || ext->ln_stat;
+  const bool any = ext->row_stat_out || ext->col_stat_out || ext->ln_rstd;
   if (!any) return AP_OK;
   if (!p.tma_epi) return fail(AP_ERR_INVALID, "gemm: epilogue statistics / LayerNorm folding need the TMA epilogue (aligned fp16 out)");
   if (ext->row_stat_out) {
@@ -839,16 +826,10 @@ static int apply_ext(GemmParams& p, const ap_epilogue_ext* ext, int epi, long lo
     p.col_stat_out = (float2*)ext->col_stat_out;
     p.col_stat_ld = ext->col_stat_ld;
   }
-  if (ext->ln_stat) {
+  if (ext->ln_rstd) {
     if (p.a_mode != A_GEMM) return fail(AP_ERR_INVALID, "gemm: LayerNorm folding only for plain GEMMs");
-    if (!ext->ln_colsum || ext->ln_parts <= 0 || ext->ln_stat_ld < m_pad)
-      return fail(AP_ERR_INVALID, "gemm: bad LayerNorm-folding arguments (parts=%d, ld=%lld)", ext->ln_parts, ext->ln_stat_ld);
-    p.ln_stat = (const float2*)ext->ln_stat;
-    p.ln_parts = ext->ln_parts;
-    p.ln_stat_ld = ext->ln_stat_ld;
-    p.ln_colsum = ext->ln_colsum;
-    p.ln_inv_k = 1.f / (float)k_ln;
-    p.ln_eps = ext->ln_eps;
+    if (p.bias == nullptr) return fail(AP_ERR_INVALID, "gemm: LayerNorm folding needs the folded bias (beta.W^T + b)");
+    p.ln_rstd = ext->ln_rstd;
   }
   return AP_OK;
 }
@@ -943,7 +924,6 @@ extern "C" int ap_gemm_f16(const void* a, long long lda, int K1, const void* a2,
     p.tma_epi = 1;
   }
   if ((rc = apply_ext(p, ext, epi, (long long)p.num_m_tiles * 128, K1))) return rc;
-  if (ext && ext->ln_stat) AP_REQUIRE(a2 == nullptr, "gemm: LayerNorm folding with a two-source A is not supported");
   return dispatch(bn, epi, cg, tmA1, tmA2, tmB, tmOut, tmRes, p, (cudaStream_t)stream);
 }
 

@@ -109,22 +109,29 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ p0, int chunks0, i
 
 // Finalize from PER-COLUMN partials written by the producing GEMM / conv epilogue (ap_gemm.cu: col_stat_out): entry e holds
 // {sum, sumsq} of every output channel over rows [32 e, 32 e + 32) of the producer's output, i.e. frame e / (HW / 32).
-// One warp per group (grid Nf, block 32 * G): lanes stride over (entry, channel of the group), double accumulation in a
-// fixed order, xor-shuffle tree -> stats[frame][group] = {mean, rstd}. The group may straddle the two concatenated sources.
-__global__ void gn_finalize_cols_kernel(const float2* __restrict__ p0, long long ld0, int C1,
-                                        const float2* __restrict__ p1, long long ld1, int epf, int cpg, int G,
-                                        double inv_count, float eps, float2* __restrict__ stats) {
+// Grid (Nf, ceil(G / 8)), block 1024 = 8 groups x 4 warps: each warp adds a quarter of the frame's entries for the channels
+// of its group (double accumulation, fixed order), xor-shuffle tree, then the four quarter sums are combined through shared
+// memory in a fixed order -> stats[frame][group] = {mean, rstd}. The group may straddle the two concatenated sources.
+__global__ void __launch_bounds__(1024)
+gn_finalize_cols_kernel(const float2* __restrict__ p0, long long ld0, int C1, const float2* __restrict__ p1, long long ld1,
+                        int epf, int cpg, int G, double inv_count, float eps, float2* __restrict__ stats) {
+  __shared__ double sh[8][4][2];
   const int frame = blockIdx.x;
-  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gl = warp >> 2, sub = warp & 3;
+  const int g = blockIdx.y * 8 + gl;
   double s = 0.0, q = 0.0;
-  const int total = epf * cpg;
-  for (int idx = lane; idx < total; idx += 32) {
-    const int e = idx / cpg;
-    const int c = g * cpg + idx % cpg;
-    const long long row = (long long)frame * epf + e;
-    const float2 v = c < C1 ? __ldg(p0 + row * ld0 + c) : __ldg(p1 + row * ld1 + (c - C1));
-    s += v.x;
-    q += v.y;
+  if (g < G) {
+    const int e0 = (epf * sub) / 4, e1 = (epf * (sub + 1)) / 4;
+    const int total = (e1 - e0) * cpg;
+    for (int idx = lane; idx < total; idx += 32) {
+      const int e = e0 + idx / cpg;
+      const int c = g * cpg + idx % cpg;
+      const long long row = (long long)frame * epf + e;
+      const float2 v = c < C1 ? __ldg(p0 + row * ld0 + c) : __ldg(p1 + row * ld1 + (c - C1));
+      s += v.x;
+      q += v.y;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -132,8 +139,15 @@ __global__ void gn_finalize_cols_kernel(const float2* __restrict__ p0, long long
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
   if (lane == 0) {
-    const double mean = s * inv_count;
-    const double var = fmax(q * inv_count - mean * mean, 0.0);
+    sh[gl][sub][0] = s;
+    sh[gl][sub][1] = q;
+  }
+  __syncthreads();
+  if (g < G && sub == 0 && lane == 0) {
+    const double S = ((sh[gl][0][0] + sh[gl][1][0]) + sh[gl][2][0]) + sh[gl][3][0];
+    const double Q = ((sh[gl][0][1] + sh[gl][1][1]) + sh[gl][2][1]) + sh[gl][3][1];
+    const double mean = S * inv_count;
+    const double var = fmax(Q * inv_count - mean * mean, 0.0);
     stats[(long long)frame * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
 }
@@ -341,6 +355,31 @@ layernormv_kernel(const __half* __restrict__ x, long long rows, int C, float eps
   }
 }
 
+// LayerNorm folding: row partials {sum, sumsq} of x (written by the producing GEMM's epilogue warps) -> the row's rstd and
+// the 8-column fp16 operand (-mean_hi, -mean_lo, -mean_hi, 0...) that carries the mean term through the tensor core.
+__global__ void ln_finalize_kernel(const float2* __restrict__ st, int parts, long long ld, long long M, float inv_k, float eps,
+                                   uint4* __restrict__ a2, float* __restrict__ rstd) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float S = 0.f, Q = 0.f;
+  for (int i = 0; i < parts; ++i) {
+    const float2 t = __ldg(st + (long long)i * ld + m);
+    S += t.x;
+    Q += t.y;
+  }
+  const float mean = S * inv_k;
+  rstd[m] = rsqrtf(fmaxf(Q * inv_k - mean * mean, 0.f) + eps);
+  const __half hi = __float2half_rn(-mean);
+  const __half lo = __float2half_rn(-mean - __half2float(hi));
+  const __half2 a = __halves2half2(hi, lo), b = __halves2half2(hi, __float2half_rn(0.f));
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a);
+  o.y = *reinterpret_cast<const uint32_t*>(&b);
+  o.z = 0u;
+  o.w = 0u;
+  a2[m] = o;
+}
+
 // Row softmax (fp16 in/out, fp32 math) for the VAE's single-head 4096-token attention, which is evaluated as
 // GEMM -> softmax -> GEMM (head dim 512 does not fit the fused attention kernel's TMEM budget). One block per row.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y,
@@ -454,14 +493,15 @@ extern "C" int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* co
   cudaStream_t stream = (cudaStream_t)stream_;
   const int C = C1 + (x2 ? C2 : 0);
   AP_REQUIRE(x && out && stats && gamma && beta && colstat1 && (!x2 || colstat2), "groupnorm_apply: null pointer");
-  AP_REQUIRE(C % groups == 0 && groups <= 32, "groupnorm_apply: C=%d groups=%d (at most 32 groups)", C, groups);
+  AP_REQUIRE(C % groups == 0, "groupnorm_apply: C=%d not divisible by groups=%d", C, groups);
   AP_REQUIRE(C1 % 8 == 0 && (!x2 || C2 % 8 == 0), "groupnorm_apply: channel counts must be multiples of 8");
   AP_REQUIRE(HW % 32 == 0, "groupnorm_apply: HW=%d must be a multiple of 32 (32-row statistics entries)", HW);
   AP_REQUIRE(ld1 >= C1 && (!x2 || ld2 >= C2), "groupnorm_apply: partial row stride smaller than the channel count");
   const int cpg = C / groups;
   float2* stat2 = reinterpret_cast<float2*>(stats);
-  gn_finalize_cols_kernel<<<Nf, 32 * groups, 0, stream>>>((const float2*)colstat1, ld1, C1, (const float2*)colstat2, ld2,
-                                                          HW / 32, cpg, groups, 1.0 / ((double)HW * (double)cpg), eps, stat2);
+  gn_finalize_cols_kernel<<<dim3(Nf, (groups + 7) / 8), 1024, 0, stream>>>(
+      (const float2*)colstat1, ld1, C1, (const float2*)colstat2, ld2, HW / 32, cpg, groups,
+      1.0 / ((double)HW * (double)cpg), eps, stat2);
   AP_CHECK_CUDA(cudaGetLastError());
   const void* srcs[2] = {x, x2};
   const int cs[2] = {C1, C2};
@@ -476,6 +516,16 @@ extern "C" int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* co
       gn_apply_kernel<false><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
                                                                        stat2, groups, gamma, beta, (__half*)out);
   }
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_layernorm_finalize_f16(const void* row_stat, int parts, long long ld, long long M, int K, float eps,
+                                         void* a2_out, float* rstd_out, void* stream) {
+  AP_REQUIRE(row_stat && a2_out && rstd_out && parts > 0 && M > 0 && K > 0 && ld >= M, "layernorm_finalize: bad arguments");
+  AP_REQUIRE((reinterpret_cast<uintptr_t>(a2_out) & 15) == 0, "layernorm_finalize: a2_out must be 16-byte aligned");
+  ln_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)row_stat, parts, ld, M, 1.f / (float)K, eps, (uint4*)a2_out, rstd_out);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }

@@ -37,15 +37,21 @@ def _tag(t, cs):
 
 
 def fold_layer_norm(w: torch.Tensor, b, gamma: torch.Tensor, beta: torch.Tensor):
-    """LN(x) W^T + b = rstd (x (W diag(gamma))^T - mean colsum) + (W beta + b). Returns (W' fp16, colsum fp32 of the ROUNDED
-    W', bias' fp32). w: [N, K] any dtype; b: [N] or None."""
+    """LN(x) W^T + b = rstd (x (W diag(gamma))^T - mean colsum) + (W beta + b). Returns (W'' fp16 [N, K + 8], bias' fp32):
+    W'' = [W diag(gamma) | cs_hi, cs_hi, cs_lo, 0 x 5] where cs = colsum of the ROUNDED W diag(gamma) split into two fp16
+    halves; multiplied by the activation operand [x | -mean_hi, -mean_lo, -mean_hi, 0 x 5] (ops.LNFold) the accumulator is
+    x W'^T - mean cs up to ~2^-22 relative (the lo x lo cross term is dropped). w: [N, K] any dtype; b: [N] or None."""
     w32 = w.detach().to(torch.float32)
-    wg = (w32 * gamma.detach().to(torch.float32)[None, :]).to(torch.float16).contiguous()
-    colsum = wg.to(torch.float32).sum(dim=1).contiguous()
+    wg = (w32 * gamma.detach().to(torch.float32)[None, :]).to(torch.float16)
+    cs = wg.to(torch.float32).sum(dim=1)
+    cs_hi = cs.to(torch.float16)
+    cs_lo = (cs - cs_hi.to(torch.float32)).to(torch.float16)
+    ext = torch.zeros(w.shape[0], ops.LN_EXTRA_K, dtype=torch.float16, device=w.device)
+    ext[:, 0], ext[:, 1], ext[:, 2] = cs_hi, cs_hi, cs_lo
     bias = w32 @ beta.detach().to(torch.float32)
     if b is not None:
         bias = bias + b.detach().to(torch.float32)
-    return wg, colsum, bias.contiguous()
+    return torch.cat([wg, ext], dim=1).contiguous(), bias.contiguous()
 
 
 class RunCtx:
@@ -100,18 +106,16 @@ class FeedForward(nn.Module):
         return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=residual, **kw)
 
     def folded(self, gamma: torch.Tensor, beta: torch.Tensor):
-        """GEGLU projection with the preceding LayerNorm (gamma, beta) folded in: (w1', colsum, b1'), value / gate rows
+        """GEGLU projection with the preceding LayerNorm (gamma, beta) folded in: (w1'' [8C, C + 8], b1'), value / gate rows
         interleaved like packed()['w1']."""
-        wg, colsum, bias = fold_layer_norm(self.net[0].proj.weight, self.net[0].proj.bias, gamma, beta)
-        w1, b1 = ops.interleave_geglu(wg, bias)
-        cs1, _ = ops.interleave_geglu(colsum[:, None], None)
-        return w1, cs1.reshape(-1).contiguous(), b1
+        wg, bias = fold_layer_norm(self.net[0].proj.weight, self.net[0].proj.bias, gamma, beta)
+        return ops.interleave_geglu(wg, bias)
 
     def run_folded(self, x: torch.Tensor, stats, fold, residual: torch.Tensor, eps: float = 1e-5, **kw) -> torch.Tensor:
         """x is the UN-normalised input; `stats` its RowStats from the producer's epilogue; fold = self.folded(...)."""
         pk = self.packed()
-        w1, cs1, b1 = fold
-        h = ops.gemm(x, w1, bias=b1, geglu=True, ln=ops.LNFold(stats, cs1, eps))
+        w1, b1 = fold
+        h = ops.gemm(x, w1, bias=b1, geglu=True, ln=ops.LNFold(stats, eps))
         return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=residual, **kw)
 
 
@@ -272,12 +276,11 @@ class BasicTransformerBlock(nn.Module):
             # norm1 folded into the q/k/v projection, norm3 into the GEGLU projection (fold_layer_norm); the padded head
             # rows stay zero (zero weight rows -> zero colsum and bias)
             qkv_w = torch.cat([self.attn1.to_q.weight, self.attn1.to_k.weight, self.attn1.to_v.weight], 0)
-            wg, cs, bias = fold_layer_norm(qkv_w, None, self.norm1.weight, self.norm1.bias)
+            wg, bias = fold_layer_norm(qkv_w, None, self.norm1.weight, self.norm1.bias)
             inner = self.heads * self.dim_head
             d["wqkv_g"] = torch.cat([ops.pad_head_rows(wg[i * inner:(i + 1) * inner], self.heads, dpad) for i in range(3)],
                                     0).contiguous()
             pad1 = lambda v: ops.pad_head_rows(v[:, None], self.heads, dpad).reshape(-1)    # noqa: E731
-            d["cs_qkv"] = torch.cat([pad1(cs[i * inner:(i + 1) * inner]) for i in range(3)]).contiguous()
             d["b_qkv"] = torch.cat([pad1(bias[i * inner:(i + 1) * inner]) for i in range(3)]).contiguous()
             d["ff_fold"] = self.ff.folded(self.norm3.weight, self.norm3.bias)
             d["eps1"], d["eps3"] = self.norm1.eps, self.norm3.eps
@@ -340,7 +343,7 @@ class BasicTransformerBlock(nn.Module):
         hp = heads * dpad
         fused = self.fused() and t0_stats is not None
         if fused:
-            qkv = ops.gemm(t0, pk["wqkv_g"], bias=pk["b_qkv"], ln=ops.LNFold(t0_stats, pk["cs_qkv"], pk["eps1"]))
+            qkv = ops.gemm(t0, pk["wqkv_g"], bias=pk["b_qkv"], ln=ops.LNFold(t0_stats, pk["eps1"]))
         else:
             n1 = ops.layer_norm(t0, pk["g1"], pk["b1"], pk["eps1"])
             if self._ref_mode == "write":
@@ -496,8 +499,8 @@ class TemporalTransformer3DModel(nn.Module):
                     pe=at.pos_encoder.pe[0].detach().to(torch.float16).to(torch.float32).contiguous()))
                 # norms[i] folded into the q/k/v projection; beta and the positional encoding become a per-frame bias table
                 qkv_w = torch.cat([at.to_q.weight, at.to_k.weight, at.to_v.weight], 0)
-                wg, cs, _ = fold_layer_norm(qkv_w, None, blk.norms[i].weight, blk.norms[i].bias)
-                d["attn"][i].update(wqkv_g=wg, cs=cs, eps=blk.norms[i].eps)
+                wg, _ = fold_layer_norm(qkv_w, None, blk.norms[i].weight, blk.norms[i].bias)
+                d["attn"][i].update(wqkv_g=wg, eps=blk.norms[i].eps)
             d["ff_fold"] = blk.ff.folded(blk.ff_norm.weight, blk.ff_norm.bias)
             d["eps_f"] = blk.ff_norm.eps
             d["pe_bias"] = {}
@@ -537,7 +540,7 @@ class TemporalTransformer3DModel(nn.Module):
             for i in range(2):
                 a = pk["attn"][i]
                 qkv = ops.gemm(m, a["wqkv_g"], bias=self._pe_bias(pk, i, ctx.B, ctx.F), bias_group_rows=n_tok,
-                               ln=ops.LNFold(st, a["cs"], a["eps"]))
+                               ln=ops.LNFold(st, a["eps"]))
                 o = ops.temporal_attention(qkv, ctx.B, ctx.F, n_tok, c, self.heads)
                 m, st = ops.gemm(o, a["wo"], bias=a["bo"], residual=m, row_stats=True)
             m = self.transformer_blocks[0].ff.run_folded(m, st, pk["ff_fold"], m, pk["eps_f"])

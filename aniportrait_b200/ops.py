@@ -75,12 +75,33 @@ class ColStats:
         self.buf = buf
 
 
-class LNFold:
-    """LayerNorm folded into the consuming GEMM: its weights are W diag(gamma), its bias beta.W^T + b, and the epilogue
-    applies rstd (acc - mean colsum) with the row statistics `stats` of the A operand."""
+LN_EXTRA_K = 8    # columns the LayerNorm folding appends to K: (-mean_hi, -mean_lo, -mean_hi, 0 x 5) x (cs_hi, cs_hi, cs_lo, 0 x 5)
 
-    def __init__(self, stats: RowStats, colsum: torch.Tensor, eps: float = 1e-5):
-        self.stats, self.colsum, self.eps = stats, colsum, eps
+
+class LNFold:
+    """LayerNorm folded into the consuming GEMM. The GEMM's weights are [W diag(gamma) | colsum_hi, colsum_hi, colsum_lo, 0..]
+    (K + LN_EXTRA_K columns: models.blocks.fold_layer_norm), its bias beta.W^T + b; `stats` are the RowStats of the A
+    operand x from its producer's epilogue. ops.gemm turns them into the [M, 8] operand (-mean_hi, -mean_lo, -mean_hi, 0..)
+    and the per-row rstd (ap_layernorm_finalize_f16), appends the operand as a second K source, and the epilogue applies
+    out = rstd * acc + bias."""
+
+    def __init__(self, stats: RowStats, eps: float = 1e-5):
+        self.stats, self.eps = stats, eps
+
+    def operands(self, M: int, K: int):
+        """(a2 [M, 8] fp16, rstd [M] fp32); computed once per RowStats."""
+        cached = getattr(self.stats, "_ln_ops", None)
+        if cached is None:
+            dev = self.stats.buf.device
+            a2 = torch.empty(M, LN_EXTRA_K, dtype=torch.float16, device=dev)
+            rstd = torch.empty(M, dtype=torch.float32, device=dev)
+            check(lib().ap_layernorm_finalize_f16(ptr(self.stats.buf), I(self.stats.parts), LL(self.stats.ld), LL(M), I(K),
+                                                  _lib.c_float(self.eps), ptr(a2), fptr(rstd), stream_ptr()),
+                  "ap_layernorm_finalize_f16")
+            _count()
+            cached = (a2, rstd)
+            self.stats._ln_ops = cached
+        return cached
 
 
 def _epilogue_ext(M, N, device, row_stats, col_stats, ln, bias, flags, K, block_n):
@@ -103,10 +124,7 @@ def _epilogue_ext(M, N, device, row_stats, col_stats, ln, bias, flags, K, block_
         cs = ColStats(torch.empty(m_pad // 32, N, 2, dtype=torch.float32, device=device))
         ext.col_stat_out, ext.col_stat_ld = cs.buf.data_ptr(), N
     if ln is not None:
-        assert ln.colsum.dtype == torch.float32 and ln.colsum.is_contiguous() and ln.colsum.numel() == N
-        assert ln.stats.ld >= m_pad
-        ext.ln_stat, ext.ln_parts, ext.ln_stat_ld = ln.stats.buf.data_ptr(), ln.stats.parts, ln.stats.ld
-        ext.ln_colsum, ext.ln_eps = ln.colsum.data_ptr(), ln.eps
+        ext.ln_rstd = ln.rstd.data_ptr()
     ext.bias_ld = bias_ld
     return ext, rs, cs
 
@@ -135,6 +153,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, res
     M, K1 = a.shape
     N = w.shape[0]
     K2 = 0
+    if ln is not None:
+        assert a2 is None and bias is not None, "LayerNorm folding: single-source A, folded bias required"
+        a2, ln.rstd = ln.operands(M, K1)
     if a2 is not None:
         assert a2.dtype == torch.float16 and a2.shape[0] == M and a2.stride(1) == 1
         K2 = a2.shape[1]

@@ -42,9 +42,10 @@ extern "C" {
  *                 parts = 2 * ap_gemm_row_stat_parts(...) ; row_stat_ld >= M rounded up to 128
  *   col_stat_out  fp32 pairs per output column over 32 consecutive rows: [ceil(M / 128) * 4][col_stat_ld]
  *                 (conv: 32-row sub-boxes of the output tile; needs Ho * Wo % 32 == 0 so that no sub-box spans two frames)
- * LayerNorm folded into this GEMM (the A operand is the un-normalised x, the weights are W diag(gamma), `bias` carries
- * beta.W^T + b): out = rstd (acc - mean * ln_colsum) + bias with {mean, rstd} of row m from the partials `ln_stat`
- * [ln_parts][ln_stat_ld] written by the producer of x, ln_colsum[n] = sum_k W'[n, k] (fp32), eps = ln_eps, K = K1.
+ * LayerNorm folded into this GEMM: A = [x | a2] with a2 = the [M, 8] fp16 matrix written by ap_layernorm_finalize_f16
+ * (columns -mean_hi, -mean_lo, -mean_hi, 0...), weights [W diag(gamma) | colsum_hi, colsum_hi, colsum_lo, 0...] (K1 + 8
+ * columns), `bias` = beta.W^T + b; the accumulator then holds x.W'^T - mean colsum(W') and the epilogue applies
+ *   out = ln_rstd[m] * acc + bias.
  *   bias_ld       row stride of the bias table in floats (0 = N): lets several ops share one [groups, sum of N] table
  */
 typedef struct ap_epilogue_ext {
@@ -52,11 +53,7 @@ typedef struct ap_epilogue_ext {
   long long row_stat_ld;
   void* col_stat_out;
   long long col_stat_ld;
-  const void* ln_stat;
-  int ln_parts;
-  long long ln_stat_ld;
-  const float* ln_colsum;
-  float ln_eps;
+  const float* ln_rstd;
   long long bias_ld;
 } ap_epilogue_ext;
 
@@ -117,6 +114,15 @@ int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int C2, int Nf,
 int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* colstat1, long long ld1, const void* x2, int C2,
                                 const void* colstat2, long long ld2, int Nf, int HW, int groups, float eps,
                                 const float* gamma, const float* beta, int silu, float* stats, void* out, void* stream);
+
+/*
+ * Row statistics -> the two small operands of a LayerNorm-folded GEMM. row_stat: fp32 pairs [parts][ld] as written by
+ * ap_epilogue_ext.row_stat_out of the op that produced x [M, K]; a2_out: fp16 [M, 8] = (-mean_hi, -mean_lo, -mean_hi, 0 x 5)
+ * (mean split into two halves so that the fp16 operand carries it to ~2^-22); rstd_out: fp32 [M] = 1 / sqrt(var + eps).
+ * Partials are added in a fixed order (bit-reproducible).
+ */
+int ap_layernorm_finalize_f16(const void* row_stat, int parts, long long ld, long long M, int K, float eps, void* a2_out,
+                              float* rstd_out, void* stream);
 
 /*
  * LayerNorm over the last dim (+ optional additive table pe[(row / rows_per_pe) % pe_period][C], the motion module's

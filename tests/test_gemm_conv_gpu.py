@@ -152,7 +152,8 @@ def test_gemm_row_stats(cuda_dev, M, N, K):
                                         (1000, 320, 2560, True), (2048, 640, 5120, True), (16384, 320, 1536, False)])
 def test_gemm_layernorm_folding(cuda_dev, M, C, N, geglu):
     """x = producer GEMM output (row statistics from its epilogue); consumer = LN(x) W^T + b (optionally GEGLU) with the
-    LayerNorm folded: weights W diag(gamma), epilogue rstd (acc - mean colsum) + (W beta + b). vs fp32 torch."""
+    LayerNorm folded: weights [W diag(gamma) | colsum], activation [x | -mean] (one extra k-block on the tensor core),
+    epilogue rstd * acc + (W beta + b). vs fp32 torch."""
     from aniportrait_b200 import ops
     from aniportrait_b200.models.blocks import fold_layer_norm
     a = _mk((M, C), cuda_dev, 1.0, 41)
@@ -166,16 +167,15 @@ def test_gemm_layernorm_folding(cuda_dev, M, C, N, geglu):
     b = (0.1 * torch.randn(N, generator=g)).to(cuda_dev)
     n = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
     ref = n @ w.half().float().t() + b
+    wg, bias = fold_layer_norm(w, b, gamma, beta)          # [N, C + 8]: W diag(gamma) | colsum (hi, hi, lo) | 0
+    assert wg.shape == (N, C + ops.LN_EXTRA_K)
     if geglu:
-        wg, cs, bias = fold_layer_norm(w, b, gamma, beta)
         wi, bi = ops.interleave_geglu(wg, bias)
-        csi, _ = ops.interleave_geglu(cs[:, None], None)
-        out = ops.gemm(x, wi, bias=bi, geglu=True, ln=ops.LNFold(rs, csi.reshape(-1).contiguous(), 1e-5))
+        out = ops.gemm(x, wi, bias=bi, geglu=True, ln=ops.LNFold(rs, 1e-5))
         half = N // 2
         ref = ref[:, :half] * F.gelu(ref[:, half:])
     else:
-        wg, cs, bias = fold_layer_norm(w, b, gamma, beta)
-        out = ops.gemm(x, wg, bias=bias, ln=ops.LNFold(rs, cs, 1e-5))
+        out = ops.gemm(x, wg, bias=bias, ln=ops.LNFold(rs, 1e-5))
     err = rel_l2(out, ref)
     print(f"LN folding M={M} C={C} N={N} geglu={geglu}: rel-L2 = {err:.3e}")
     assert err < 3e-3

@@ -334,16 +334,22 @@ def test_layernorm_folding_algebra():
     x = torch.randn(M, C, generator=g) + 0.4
     w, b = torch.randn(N, C, generator=g) * C ** -0.5, torch.randn(N, generator=g) * 0.1
     gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
-    wg, cs, bias = fold_layer_norm(w, b, gamma, beta)
+    wg, bias = fold_layer_norm(w, b, gamma, beta)                       # [N, C + 8]
+    assert wg.shape == (N, C + ops.LN_EXTRA_K)
     mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
     rstd = (var + 1e-5).rsqrt()
-    got = rstd * (x @ wg.float().t() - mean * cs[None]) + bias[None]
+
+    def a_ext(t, mean):      # what ap_layernorm_finalize_f16 appends: -mean split in two fp16 halves, (hi, lo, hi, 0 x 5)
+        hi = (-mean).half()
+        lo = (-mean - hi.float()).half()
+        return torch.cat([t, hi.float(), lo.float(), hi.float(), torch.zeros(t.shape[0], 5)], 1)
+    got = rstd * (a_ext(x, mean) @ wg.float().t()) + bias[None]
     ref = F.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b
     assert rel_l2(got, ref) < 2e-3          # W' is rounded to fp16
     # GEGLU: the folded, interleaved projection pairs value / gate columns like the kernel's epilogue expects
     ff = FeedForward(C)
-    w1, cs1, b1 = ff.folded(gamma, beta)
-    acc = rstd * (x @ w1.float().t() - mean * cs1[None]) + b1[None]                      # [M, 8C] interleaved 16 | 16
+    w1, b1 = ff.folded(gamma, beta)
+    acc = rstd * (a_ext(x, mean) @ w1.float().t()) + b1[None]                              # [M, 8C] interleaved 16 | 16
     a = acc.view(M, -1, 2, 16)
     got = (a[:, :, 0] * F.gelu(a[:, :, 1])).reshape(M, -1)
     h, gate = (F.layer_norm(x, (C,), gamma, beta, 1e-5) @ ff.net[0].proj.weight.t() + ff.net[0].proj.bias).chunk(2, -1)
@@ -354,12 +360,12 @@ def test_layernorm_folding_algebra():
         torch.nn.init.normal_(p, std=0.3)
     pk = mm.packed()
     B, Fr, n_tok = 2, 5, 3
-    m = torch.randn(B * Fr * n_tok, C, generator=g)
+    m = torch.randn(B * Fr * n_tok, C, generator=g) + 0.7
     a0 = pk["attn"][0]
     tab = mm._pe_bias(pk, 0, B, Fr)                                                        # [B*F, 3C]
     mean, rstd = m.mean(1, keepdim=True), (m.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
     rows = torch.arange(B * Fr * n_tok) // n_tok
-    got = rstd * (m @ a0["wqkv_g"].float().t() - mean * a0["cs"][None]) + tab[rows]
+    got = rstd * (a_ext(m, mean) @ a0["wqkv_g"].float().t()) + tab[rows]
     frame = rows % Fr
     n = F.layer_norm(m, (C,), a0["g"], a0["b"], 1e-5) + a0["pe"][frame]
     assert rel_l2(got, n @ a0["wqkv"].float().t()) < 2e-3
