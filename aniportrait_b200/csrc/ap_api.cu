@@ -1,6 +1,7 @@
 // C-ABI plumbing: version, error string, device binding, TMA descriptor encoding.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ap_host.h"
@@ -35,6 +36,13 @@ static int resolve_driver() {
 }
 
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+bool pdl_enabled() {
+  // measured on one box (profiles/r02_summary.md): UNet3D call 48.16 ms with, 47.57 ms without; 12.32 vs 12.34 frames/s ->
+  // no gain (the kernel-to-kernel gap inside a replayed graph is not launch latency), so it is opt-in
+  static const bool on = getenv("AP_PDL") && atoi(getenv("AP_PDL")) != 0;
+  return on;
+}
 
 int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box, bool swizzle128, int elem_bytes, int swizzle_bytes) {

@@ -67,7 +67,6 @@ struct AttnParams {
   float scale_log2;       // softmax scale * log2(e)
   __half* out;
   long long ldo;
-  int stagger_clk;        // v5: start-up delay of the softmax warps of every second CTA of an SM (see attention5_kernel)
 };
 
 // Row maximum with the 3-input FMNMX3 of sm_100 (half the instructions of a 2-input reduction).
@@ -94,8 +93,6 @@ __device__ __forceinline__ float row_max(const uint32_t* sr) {
   return fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]), fmaxf(m[6], m[7]));
 }
 
-// Per-SM arrival counter of attention5 CTAs (two are co-resident per SM; parity = which of the two a CTA is).
-__device__ unsigned int g_attn5_sm_arrivals[1024];
 
 template <int DPAD, int BN>
 struct AttnCfg {
@@ -122,6 +119,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
   using Cfg = AttnCfg<DPAD, BN>;
   constexpr int ST = Cfg::STAGES;
+  griddep_launch_dependents();   // PDL (ap_host.h::launch_pdl)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
@@ -166,6 +164,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();   // PDL: Q/K/V come from the previous kernel
 
   const int own_tiles = (p.tokens + BN - 1) / BN;
   const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
@@ -434,6 +433,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
   using Cfg = Attn3Cfg<DPAD, BN>;
   constexpr int ST = Cfg::STAGES;
+  griddep_launch_dependents();   // PDL (ap_host.h::launch_pdl)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
@@ -475,6 +475,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();   // PDL: Q/K/V come from the previous kernel
 
   const int own_tiles = (p.tokens + BN - 1) / BN;
   const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
@@ -721,7 +722,7 @@ static int launch_attention3(const CUtensorMap* maps, const AttnParams& p, cudaS
   }
   const int units = p.n_frames * p.heads * ((p.tokens + 255) / 256);
   const int grid = units < num_sms() ? units : num_sms();
-  attention3_kernel<DPAD, BN><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
+  AP_LAUNCH((attention3_kernel<DPAD, BN>), grid, 320, Cfg::SMEM_BYTES, stream, maps[0], maps[1], maps[2],
                                                                                          maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -752,6 +753,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
   using Cfg = Attn5Cfg;
   constexpr int ST = Cfg::STAGES, BN = Cfg::BN, DPAD = Cfg::DPAD;
+  griddep_launch_dependents();   // PDL (ap_host.h::launch_pdl)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
@@ -767,7 +769,6 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* pv_done = p_full + 2;         // every P.V (rescale path only)
   uint64_t* o_done = pv_done + 1;         // last P.V of a unit
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
-  uint32_t* slot_ptr = tmem_ptr + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -790,16 +791,13 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_init(pv_done, 1);
     mbar_init(o_done, 1);
     fence_mbar_init();
-    // which of the SM's two co-resident CTAs is this one? (every launch adds exactly two arrivals per SM: parity is enough)
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    *slot_ptr = atomicAdd(&g_attn5_sm_arrivals[smid & 1023], 1u) & 1u;
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();   // PDL: Q/K/V come from the previous kernel
 
   const int own_tiles = (p.tokens + BN - 1) / BN;
   const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
@@ -903,16 +901,9 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t t_o = tmem_base + Cfg::TMEM_O + t_lane;
     uint32_t g = 0, uc = 0;
     uint32_t sr[BN];
-    // Anti-phase start. Per key tile a softmax warp spends ~2/3 of its time in the MUFU-bound exponential loop and ~1/3 in
-    // phases without exponentials (S load, row maximum, P store, barrier). The two CTAs of an SM run the same schedule on
-    // the same kind of unit; launched together they stay IN phase (the phase difference of two such warps sharing the MUFU
-    // pipe is neutrally stable), so their exponential loops collide and their idle phases coincide: XU pipe 70 % busy.
-    // Delaying the softmax warps of every second CTA by about one idle phase interleaves them instead.
-    if (p.stagger_clk > 0 && *slot_ptr != 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.stagger_clk) {
-      }
-    }
+    // (Round 2: delaying the softmax warps of every second CTA of an SM by 400..1400 clocks, and halving the row-maximum
+    // instructions with FMNMX3, both left the launch at 2.22 ms: the phases without exponentials are already hidden and the
+    // two co-resident CTAs are not phase-locked; profiles/r02_summary.md.)
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
       int frame, head, m_tile, T;
       decode(unit, frame, head, m_tile, T);
@@ -1026,7 +1017,7 @@ static int launch_attention5(const CUtensorMap* maps, const AttnParams& p, cudaS
   }
   const int max_ctas = 2 * num_sms();
   const int grid = p.num_units < max_ctas ? p.num_units : max_ctas;
-  attention5_kernel<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  AP_LAUNCH((attention5_kernel), grid, 192, Cfg::SMEM_BYTES, stream, maps[0], maps[1], maps[2], maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -1041,7 +1032,7 @@ static int launch_attention(const CUtensorMap* maps, const AttnParams& p, cudaSt
     attr_set = true;
   }
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  attention_kernel<DPAD, BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  AP_LAUNCH((attention_kernel<DPAD, BN>), grid, 192, Cfg::SMEM_BYTES, stream, maps[0], maps[1], maps[2], maps[3], maps[4], p);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -1089,8 +1080,6 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = (__half*)out;
   p.ldo = ldo;
-  static const int stagger_env = getenv("AP_ATTN_STAGGER") ? atoi(getenv("AP_ATTN_STAGGER")) : 700;
-  p.stagger_clk = stagger_env;
   if (has_bank) {
     const int max_bank = (n_frames - 1 - first_bank_frame) / frames_per_bank;
     AP_REQUIRE(first_bank_frame >= n_frames || max_bank < n_banks, "attention: bank index out of range");

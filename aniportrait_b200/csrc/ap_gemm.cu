@@ -128,6 +128,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             const __grid_constant__ CUtensorMap tmRes, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG, NACC>;
   constexpr int STAGES = Cfg::STAGES;
+  griddep_launch_dependents();   // PDL: the next kernel may be scheduled; it waits for this one in ITS griddep_wait()
   // CG == 2: the CTAs of a pair (cluster of 2) work on two vertically adjacent 128-row tiles with ONE M=256 MMA issued
   // by the leader (rank 0). `cta_rank` selects this CTA's A rows and its half of the B tile.
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
@@ -177,6 +178,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above (barriers, TMEM, descriptor prefetch) is independent of the previous kernel's data; from here on the
+  // TMA loads / epilogue reads touch it: wait until the previous kernel of the stream has completed (PDL)
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane
@@ -691,22 +695,10 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
   const int items = (p.num_m_tiles / CG) * (p.num_n_tiles / NACC);
   const int max_ctas = (num_sms() / CG) * CG;
   const int grid = items * CG < max_ctas ? items * CG : max_ctas;
-  if (CG == 1) {
-    gemm_kernel<BN, EPI, CG, NACC><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(a1, a2, b, to, tr, p);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(320);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG, NACC>, a1, a2, b, to, tr, p));
+  {
+    cudaError_t le = launch_pdl(gemm_kernel<BN, EPI, CG, NACC>, dim3(grid), dim3(320), (size_t)Cfg::SMEM_BYTES, stream, CG, a1,
+                                a2, b, to, tr, p);
+    if (le != cudaSuccess) return fail(AP_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(le));
   }
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;

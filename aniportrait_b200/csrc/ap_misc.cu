@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "ap_host.h"
+#include "ap_ptx.cuh"
 
 namespace ap {
 
@@ -17,6 +18,8 @@ template <int FP, int VEC>  // FP: frames padded to a power of two (4, 8, 16, 32
 __global__ void __launch_bounds__(256)
 temporal_attn_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int B,
                      int F, int N, int C, int heads, float scale) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   constexpr int PW = 32 / FP;  // positions per warp
   constexpr int CH = 8 * VEC;
   const int warp = threadIdx.x >> 5;
@@ -187,6 +190,8 @@ template <int D>
 __global__ void __launch_bounds__(32 * (TA_GC / D))
 temporal_attn_mma_kernel(const __half* __restrict__ qkv, long long ld, __half* __restrict__ out, long long ldo, int F,
                          int N, int C, float scale_log2) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   constexpr int HG = TA_GC / D;        // heads (= warps) per block
   constexpr int NT = 32 * HG;
   constexpr int SEG_V = TA_GC / 8;     // uint4 per 640-byte segment
@@ -313,6 +318,8 @@ temporal_attn_mma_kernel(const __half* __restrict__ qkv, long long ld, __half* _
 // ---------------------------------------------------------------------------------------------------------
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
                            long long nvec) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; idx < nvec; idx += stride) {
@@ -332,6 +339,8 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
 
 __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o,
                                  long long nvec, long long nbvec) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; idx < nvec; idx += stride) {
@@ -350,6 +359,8 @@ __global__ void add_bcast_kernel(const uint4* __restrict__ a, const uint4* __res
 }
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= B * half) return;
@@ -361,6 +372,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 }
 
 __global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) {
     const float v = __half2float(x[idx]);
@@ -371,6 +384,8 @@ __global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y
 // nearest-neighbour 2x upsample, channels-last: out[n, y, x, :] = in[n, y/2, x/2, :]
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int Nf, int H, int W,
                                   int cvec) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long total = (long long)Nf * 2 * H * 2 * W * cvec;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -388,6 +403,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 // [B, C, F, H, W] (reference layout) -> [(b f), H, W, Cpad] channels-last, zero padded channels
 __global__ void ncfhw_to_nhwc_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int F,
                                      int HW, int Cpad) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long total = (long long)B * F * HW * Cpad;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -405,6 +422,8 @@ __global__ void ncfhw_to_nhwc_kernel(const __half* __restrict__ in, __half* __re
 // [(b f), HW, ld] channels-last (first C channels) -> [B, C, F, H, W]
 __global__ void nhwc_to_ncfhw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int F,
                                      int HW, int ld) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long total = (long long)B * C * F * HW;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -426,6 +445,8 @@ __global__ void nhwc_to_ncfhw_kernel(const __half* __restrict__ in, __half* __re
 // UNet input for one window: out[(b, f), px, 0..Cpad) = latents[idx[f], px, 0..4) duplicated over `dup` CFG branches
 __global__ void gather_window_kernel(const __half* __restrict__ lat, const int* __restrict__ idx, __half* __restrict__ out,
                                      int dup, int F, int HW, int Cpad) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long total = (long long)dup * F * HW;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -443,6 +464,8 @@ __global__ void gather_window_kernel(const __half* __restrict__ lat, const int* 
 // (pipeline_pose2vid_long.py:546-547), and race-free.
 __global__ void scatter_accumulate_kernel(const __half* __restrict__ pred, int ld, const int* __restrict__ idx,
                                           float* __restrict__ acc, int B, int F, int L, int HW) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long total = (long long)B * F * HW;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -465,6 +488,8 @@ __global__ void scatter_accumulate_kernel(const __half* __restrict__ pred, int l
 __global__ void cfg_ddim_step_kernel(float* __restrict__ acc, const float* __restrict__ inv_count, int cfg, float guidance,
                                      float c_xx, float c_xv, float c_ex, float c_ev, float clip, float sqrt_ap,
                                      float sqrt_bp, __half* __restrict__ lat, int L, int HW) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long total = (long long)L * HW * 4;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -510,9 +535,9 @@ extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* ou
   if (!force_scalar && F <= 16 && C % TA_GC == 0 && heads * d == C && (d == 40 || d == 80 || d == 160)) {
     const unsigned grid = (unsigned)((long long)B * N * (C / TA_GC));
     const float sl2 = scale * 1.4426950408889634f;
-    if (d == 40) temporal_attn_mma_kernel<40><<<grid, 256, 0, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
-    else if (d == 80) temporal_attn_mma_kernel<80><<<grid, 128, 0, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
-    else temporal_attn_mma_kernel<160><<<grid, 64, 0, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
+    if (d == 40) AP_LAUNCH((temporal_attn_mma_kernel<40>), grid, 256, 0, stream, (const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
+    else if (d == 80) AP_LAUNCH((temporal_attn_mma_kernel<80>), grid, 128, 0, stream, (const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
+    else AP_LAUNCH((temporal_attn_mma_kernel<160>), grid, 64, 0, stream, (const __half*)qkv, ld, (__half*)out, ldo, F, N, C, sl2);
     AP_CHECK_CUDA(cudaGetLastError());
     return AP_OK;
   }
@@ -524,7 +549,7 @@ extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* ou
   const long long groups = (long long)B * ((N + PW - 1) / PW);
   const size_t smem = (size_t)8 * 2 * PW * FP * (8 * VEC) * sizeof(__half);
 #define AP_T(FP_, V_)                                                                                             \
-  temporal_attn_kernel<FP_, V_><<<(unsigned)groups, 256, smem, stream>>>((const __half*)qkv, ld, (__half*)out, ldo, B, \
+  AP_LAUNCH((temporal_attn_kernel<FP_, V_>), (unsigned)groups, 256, smem, stream, (const __half*)qkv, ld, (__half*)out, ldo, B, \
                                                                          F, N, C, heads, scale)
 #define AP_TV(FP_)                      \
   do {                                  \
@@ -545,14 +570,14 @@ extern "C" int ap_temporal_attention_f16(const void* qkv, long long ld, void* ou
 
 extern "C" int ap_add_f16(const void* a, const void* b, void* out, long long n, void* stream) {
   AP_REQUIRE(a && b && out && n % 8 == 0, "add: n must be a multiple of 8");
-  add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  AP_LAUNCH((add_kernel), grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, (const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
 
 extern "C" int ap_add_bcast_f16(const void* a, const void* b, void* out, long long n, long long nb, void* stream) {
   AP_REQUIRE(a && b && out && n % 8 == 0 && nb % 8 == 0 && nb > 0 && n % nb == 0, "add_bcast: bad sizes");
-  add_bcast_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+  AP_LAUNCH((add_bcast_kernel), grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, (const uint4*)a, (const uint4*)b, (uint4*)out,
                                                                          n / 8, nb / 8);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -561,14 +586,14 @@ extern "C" int ap_add_bcast_f16(const void* a, const void* b, void* out, long lo
 extern "C" int ap_timestep_embedding_f16(const float* t, int B, int dim, void* out, void* stream) {
   AP_REQUIRE(t && out && dim % 2 == 0, "timestep_embedding: bad arguments");
   const int n = B * dim / 2;
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, B, dim, (__half*)out);
+  AP_LAUNCH((timestep_embedding_kernel), (n + 127) / 128, 128, 0, (cudaStream_t)stream, t, B, dim, (__half*)out);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
 
 extern "C" int ap_silu_f16(const void* x, void* out, long long n, void* stream) {
   AP_REQUIRE(x && out, "silu: null pointer");
-  silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, n);
+  AP_LAUNCH((silu_kernel), (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, n);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -576,7 +601,7 @@ extern "C" int ap_silu_f16(const void* x, void* out, long long n, void* stream) 
 extern "C" int ap_upsample2x_nhwc_f16(const void* x, void* out, int Nf, int H, int W, int C, void* stream) {
   AP_REQUIRE(x && out && C % 8 == 0, "upsample2x: C must be a multiple of 8");
   const long long total = (long long)Nf * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, Nf, H, W, C / 8);
+  AP_LAUNCH((upsample2x_kernel), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)out, Nf, H, W, C / 8);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -584,7 +609,7 @@ extern "C" int ap_upsample2x_nhwc_f16(const void* x, void* out, int Nf, int H, i
 extern "C" int ap_ncfhw_to_nhwc_f16(const void* x, void* out, int B, int C, int F, int HW, int Cpad, void* stream) {
   AP_REQUIRE(x && out && Cpad >= C, "ncfhw_to_nhwc: bad arguments");
   const long long total = (long long)B * F * HW * Cpad;
-  ncfhw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, B, C, F, HW, Cpad);
+  AP_LAUNCH((ncfhw_to_nhwc_kernel), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, B, C, F, HW, Cpad);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -592,7 +617,7 @@ extern "C" int ap_ncfhw_to_nhwc_f16(const void* x, void* out, int B, int C, int 
 extern "C" int ap_nhwc_to_ncfhw_f16(const void* x, void* out, int B, int C, int F, int HW, int ld, void* stream) {
   AP_REQUIRE(x && out && ld >= C, "nhwc_to_ncfhw: bad arguments");
   const long long total = (long long)B * C * F * HW;
-  nhwc_to_ncfhw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, B, C, F, HW, ld);
+  AP_LAUNCH((nhwc_to_ncfhw_kernel), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, B, C, F, HW, ld);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -601,7 +626,7 @@ extern "C" int ap_gather_window_f16(const void* latents, const int* frame_idx, v
                                     int Cpad, void* stream) {
   AP_REQUIRE(latents && frame_idx && out && Cpad % 8 == 0 && Cpad >= 8, "gather_window: bad arguments");
   const long long total = (long long)dup * F * HW;
-  gather_window_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  AP_LAUNCH((gather_window_kernel), (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, 
       (const __half*)latents, frame_idx, (__half*)out, dup, F, HW, Cpad);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -611,7 +636,7 @@ extern "C" int ap_scatter_accumulate_f16(const void* pred, int ld, const int* fr
                                          int L, int HW, void* stream) {
   AP_REQUIRE(pred && frame_idx && acc, "scatter_accumulate: null pointer");
   const long long total = (long long)B * F * HW;
-  scatter_accumulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  AP_LAUNCH((scatter_accumulate_kernel), (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, 
       (const __half*)pred, ld, frame_idx, acc, B, F, L, HW);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -635,7 +660,7 @@ extern "C" int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg,
     return ap::fail(AP_ERR_INVALID, "cfg_ddim_step: unknown prediction_type %d", prediction_type);
   }
   const long long total = (long long)L * HW * 4;
-  cfg_ddim_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  AP_LAUNCH((cfg_ddim_step_kernel), (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, 
       acc, inv_count, cfg, guidance, c_xx, c_xv, c_ex, c_ev, clip_range, sqrtf(alpha_prev), sqrtf(1.f - alpha_prev),
       (__half*)latents, L, HW);
   AP_CHECK_CUDA(cudaGetLastError());

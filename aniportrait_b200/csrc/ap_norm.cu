@@ -8,6 +8,7 @@
 #include <stdlib.h>
 
 #include "ap_host.h"
+#include "ap_ptx.cuh"
 
 namespace ap {
 
@@ -21,6 +22,8 @@ namespace ap {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int c_off, int cpg, int rows_per_block,
                                 float2* __restrict__ partials, int G) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int vecs = C >> 3;
   const int k = blockDim.x / vecs;
   const int cv = threadIdx.x % vecs;
@@ -80,6 +83,8 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int
 __global__ void gn_finalize_kernel(const float2* __restrict__ p0, int chunks0, int glo0, int ghi0,
                                    const float2* __restrict__ p1, int chunks1, int glo1, int ghi1, int G,
                                    double inv_count, float eps, float2* __restrict__ stats) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int frame = blockIdx.x;
   const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
   double s = 0.0, q = 0.0;
@@ -115,6 +120,8 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ p0, int chunks0, i
 __global__ void __launch_bounds__(1024)
 gn_finalize_cols_kernel(const float2* __restrict__ p0, long long ld0, int C1, const float2* __restrict__ p1, long long ld1,
                         int epf, int cpg, int G, double inv_count, float eps, float2* __restrict__ stats) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   __shared__ double sh[8][4][2];
   const int frame = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,6 +175,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int
                                 int rows_per_block, const float2* __restrict__ stats, int G,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __half* __restrict__ y) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int vecs = C >> 3;
   const int k = blockDim.x / vecs;
   const int cv = threadIdx.x % vecs;
@@ -218,6 +227,8 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long rows, i
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ pe, int rows_per_pe, int pe_period,
                                  __half* __restrict__ y) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int warps_per_block = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -279,6 +290,8 @@ __global__ void __launch_bounds__(256)
 layernormv_kernel(const __half* __restrict__ x, long long rows, int C, float eps, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const float* __restrict__ pe, int rows_per_pe, int pe_period,
                   __half* __restrict__ y) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   constexpr int MAXV = 6;
   constexpr int RPW = 32 / LPR;   // rows per warp
   const int lane = threadIdx.x & 31;
@@ -359,6 +372,8 @@ layernormv_kernel(const __half* __restrict__ x, long long rows, int C, float eps
 // the 8-column fp16 operand (-mean_hi, -mean_lo, -mean_hi, 0...) that carries the mean term through the tensor core.
 __global__ void ln_finalize_kernel(const float2* __restrict__ st, int parts, long long ld, long long M, float inv_k, float eps,
                                    uint4* __restrict__ a2, float* __restrict__ rstd) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float S = 0.f, Q = 0.f;
@@ -384,6 +399,8 @@ __global__ void ln_finalize_kernel(const float2* __restrict__ st, int parts, lon
 // GEMM -> softmax -> GEMM (head dim 512 does not fit the fused attention kernel's TMEM budget). One block per row.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                            int cols, long long ld) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const long long row = blockIdx.x;
   const __half2* src = reinterpret_cast<const __half2*>(x + row * ld);
   __half2* dst = reinterpret_cast<__half2*>(y + row * ld);
@@ -463,21 +480,21 @@ extern "C" int ap_groupnorm_nhwc_f16(const void* x, int C1, const void* x2, int 
     const int k = threads[s] / (cs[s] / 8);
     AP_REQUIRE((size_t)(k + 1) * cs[s] * sizeof(float2) <= 48 * 1024, "groupnorm: C=%d too wide for the reduction buffer", cs[s]);
     if (s == 0) part[1] = part[0] + (long long)Nf * chunks[0] * groups;
-    gn_stats_kernel<<<dim3(chunks[s], Nf), threads[s], sizeof(float2) * (k + 1) * cs[s], stream>>>(
+    AP_LAUNCH((gn_stats_kernel), dim3(chunks[s], Nf), threads[s], sizeof(float2) * (k + 1) * cs[s], stream, 
         (const __half*)srcs[s], HW, cs[s], offs[s], cpg, rpb[s], part[s], groups);
   }
   AP_CHECK_CUDA(cudaGetLastError());
   const double inv_count = 1.0 / ((double)HW * (double)cpg);
-  gn_finalize_kernel<<<Nf, 8 * groups, 0, stream>>>(part[0], chunks[0], 0, (C1 - 1) / cpg, part[1], nsrc == 2 ? chunks[1] : 0,
+  AP_LAUNCH((gn_finalize_kernel), Nf, 8 * groups, 0, stream, part[0], chunks[0], 0, (C1 - 1) / cpg, part[1], nsrc == 2 ? chunks[1] : 0,
                                                    C1 / cpg, (C - 1) / cpg, groups, inv_count, eps, stat2);
   AP_CHECK_CUDA(cudaGetLastError());
   for (int s = 0; s < nsrc; ++s) {
     if (silu)
-      gn_apply_kernel<true><<<dim3(chunks[s], Nf), threads[s], 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
+      AP_LAUNCH((gn_apply_kernel<true>), dim3(chunks[s], Nf), threads[s], 0, stream, (const __half*)srcs[s], HW, cs[s], offs[s], C,
                                                                             cpg, rpb[s], stat2, groups, gamma, beta,
                                                                             (__half*)out);
     else
-      gn_apply_kernel<false><<<dim3(chunks[s], Nf), threads[s], 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C,
+      AP_LAUNCH((gn_apply_kernel<false>), dim3(chunks[s], Nf), threads[s], 0, stream, (const __half*)srcs[s], HW, cs[s], offs[s], C,
                                                                              cpg, rpb[s], stat2, groups, gamma, beta,
                                                                              (__half*)out);
   }
@@ -499,7 +516,7 @@ extern "C" int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* co
   AP_REQUIRE(ld1 >= C1 && (!x2 || ld2 >= C2), "groupnorm_apply: partial row stride smaller than the channel count");
   const int cpg = C / groups;
   float2* stat2 = reinterpret_cast<float2*>(stats);
-  gn_finalize_cols_kernel<<<dim3(Nf, (groups + 7) / 8), 1024, 0, stream>>>(
+  AP_LAUNCH((gn_finalize_cols_kernel), dim3(Nf, (groups + 7) / 8), 1024, 0, stream, 
       (const float2*)colstat1, ld1, C1, (const float2*)colstat2, ld2, HW / 32, cpg, groups,
       1.0 / ((double)HW * (double)cpg), eps, stat2);
   AP_CHECK_CUDA(cudaGetLastError());
@@ -510,10 +527,10 @@ extern "C" int ap_groupnorm_apply_nhwc_f16(const void* x, int C1, const void* co
     int threads, rpb, chunks;
     gn_launch_geometry(HW, cs[s], Nf, &threads, &rpb, &chunks);
     if (silu)
-      gn_apply_kernel<true><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
+      AP_LAUNCH((gn_apply_kernel<true>), dim3(chunks, Nf), threads, 0, stream, (const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
                                                                       stat2, groups, gamma, beta, (__half*)out);
     else
-      gn_apply_kernel<false><<<dim3(chunks, Nf), threads, 0, stream>>>((const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
+      AP_LAUNCH((gn_apply_kernel<false>), dim3(chunks, Nf), threads, 0, stream, (const __half*)srcs[s], HW, cs[s], offs[s], C, cpg, rpb,
                                                                        stat2, groups, gamma, beta, (__half*)out);
   }
   AP_CHECK_CUDA(cudaGetLastError());
@@ -524,7 +541,7 @@ extern "C" int ap_layernorm_finalize_f16(const void* row_stat, int parts, long l
                                          void* a2_out, float* rstd_out, void* stream) {
   AP_REQUIRE(row_stat && a2_out && rstd_out && parts > 0 && M > 0 && K > 0 && ld >= M, "layernorm_finalize: bad arguments");
   AP_REQUIRE((reinterpret_cast<uintptr_t>(a2_out) & 15) == 0, "layernorm_finalize: a2_out must be 16-byte aligned");
-  ln_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  AP_LAUNCH((ln_finalize_kernel), (unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream, 
       (const float2*)row_stat, parts, ld, M, 1.f / (float)K, eps, (uint4*)a2_out, rstd_out);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -532,7 +549,7 @@ extern "C" int ap_layernorm_finalize_f16(const void* row_stat, int parts, long l
 
 extern "C" int ap_softmax_rows_f16(const void* x, void* out, long long rows, int cols, long long ld, void* stream) {
   AP_REQUIRE(x && out && cols % 2 == 0 && ld % 2 == 0, "softmax_rows: cols/ld must be even");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, cols, ld);
+  AP_LAUNCH((softmax_rows_kernel), (unsigned)rows, 256, 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, cols, ld);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
@@ -550,7 +567,7 @@ extern "C" int ap_layernorm_f16(const void* x, long long rows, int C, float eps,
     const int lpr = nvec <= 6 * 8 ? 8 : (nvec <= 6 * 16 ? 16 : 32);
     const unsigned gridv = (unsigned)((rows + (32 / lpr) * wpb - 1) / ((32 / lpr) * wpb));
 #define AP_LNV(L)                                                                                                        \
-  layernormv_kernel<L><<<gridv, wpb * 32, 0, stream>>>((const __half*)x, rows, C, eps, gamma, beta, pe,                   \
+  AP_LAUNCH((layernormv_kernel<L>), gridv, wpb * 32, 0, stream, (const __half*)x, rows, C, eps, gamma, beta, pe,                   \
                                                        rows_per_pe > 0 ? rows_per_pe : 1, pe_period > 0 ? pe_period : 1, \
                                                        (__half*)out)
     if (lpr == 8) AP_LNV(8);
@@ -563,7 +580,7 @@ extern "C" int ap_layernorm_f16(const void* x, long long rows, int C, float eps,
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   const int maxv = (C / 2 + 31) / 32;
 #define AP_LN(MV)                                                                                              \
-  layernorm_kernel<MV><<<grid, wpb * 32, 0, stream>>>((const __half*)x, rows, C, eps, gamma, beta, pe,          \
+  AP_LAUNCH((layernorm_kernel<MV>), grid, wpb * 32, 0, stream, (const __half*)x, rows, C, eps, gamma, beta, pe,          \
                                                       rows_per_pe > 0 ? rows_per_pe : 1, pe_period > 0 ? pe_period : 1, \
                                                       (__half*)out)
   if (maxv <= 5) AP_LN(5);

@@ -10,6 +10,7 @@
 // activation for the BatchNorm apply, one extra read for its statistics. Reductions are two-stage and order-fixed (no
 // floating-point atomics), so results are bit-reproducible.
 #include "ap_host.h"
+#include "ap_ptx.cuh"
 
 namespace ap {
 
@@ -21,6 +22,8 @@ namespace ap {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void bn_stats_kernel(const __half* __restrict__ x, long long rows, int C, int rows_per_block,
                                 float2* __restrict__ partials) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int vecs = C >> 3;
   const int k = blockDim.x / vecs;
   const int cv = threadIdx.x % vecs;
@@ -64,6 +67,8 @@ __global__ void bn_stats_kernel(const __half* __restrict__ x, long long rows, in
 __global__ void bn_finalize_kernel(const float2* __restrict__ partials, int chunks, int C, double inv_rows, float eps,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float2* __restrict__ ab) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
@@ -81,6 +86,8 @@ __global__ void bn_finalize_kernel(const float2* __restrict__ partials, int chun
 template <bool RELU>
 __global__ void bn_apply_kernel(const __half* __restrict__ x, long long n_vec, int C, const float2* __restrict__ ab,
                                 __half* __restrict__ y) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   const int vecs = C >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % vecs) * 8;
@@ -113,6 +120,8 @@ template <int CIN, int K, int S, int COUT_T>
 __global__ void __launch_bounds__(128)
 conv_direct_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                    __half* __restrict__ out, int Nf, int H, int W, int Ho, int Wo, int Cout, int pad) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
   __shared__ __align__(16) float ws[K * K * CIN * COUT_T];
   const int co0 = blockIdx.y * COUT_T;
   for (int i = threadIdx.x; i < K * K * CIN * COUT_T; i += blockDim.x) {
@@ -183,7 +192,7 @@ static int launch_conv_direct(const void* x, const void* w, const float* bias, v
                               int Wo, int Cout, int pad, cudaStream_t stream) {
   const long long total = (long long)Nf * Ho * Wo;
   dim3 grid((unsigned)((total + 127) / 128), (unsigned)(Cout / COUT_T));
-  conv_direct_kernel<CIN, K, S, COUT_T><<<grid, 128, 0, stream>>>((const __half*)x, (const __half*)w, bias, (__half*)out,
+  AP_LAUNCH((conv_direct_kernel<CIN, K, S, COUT_T>), grid, 128, 0, stream, (const __half*)x, (const __half*)w, bias, (__half*)out,
                                                                   Nf, H, W, Ho, Wo, Cout, pad);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
@@ -214,15 +223,15 @@ extern "C" int ap_batchnorm_train_nhwc_f16(const void* x, long long rows, int C,
              "batchnorm: workspace too small (%lld floats needed)", 2LL * ((long long)chunks * C + C));
   float2* partials = reinterpret_cast<float2*>(workspace);
   float2* ab = partials + (long long)chunks * C;
-  bn_stats_kernel<<<chunks, threads, sizeof(float2) * (size_t)k * C, stream>>>((const __half*)x, rows, C, (int)rpb, partials);
+  AP_LAUNCH((bn_stats_kernel), chunks, threads, sizeof(float2) * (size_t)k * C, stream, (const __half*)x, rows, C, (int)rpb, partials);
   AP_CHECK_CUDA(cudaGetLastError());
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, chunks, C, 1.0 / (double)rows, eps, gamma, beta, ab);
+  AP_LAUNCH((bn_finalize_kernel), (C + 127) / 128, 128, 0, stream, partials, chunks, C, 1.0 / (double)rows, eps, gamma, beta, ab);
   AP_CHECK_CUDA(cudaGetLastError());
   const long long n_vec = rows * vecs;
   long long blocks = (n_vec + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  if (relu) bn_apply_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)x, n_vec, C, ab, (__half*)out);
-  else bn_apply_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)x, n_vec, C, ab, (__half*)out);
+  if (relu) AP_LAUNCH((bn_apply_kernel<true>), (unsigned)blocks, 256, 0, stream, (const __half*)x, n_vec, C, ab, (__half*)out);
+  else AP_LAUNCH((bn_apply_kernel<false>), (unsigned)blocks, 256, 0, stream, (const __half*)x, n_vec, C, ab, (__half*)out);
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }
