@@ -39,7 +39,28 @@ def lin():
     ops.gemm(a, w2, bias=b, residual=res, out=o2)
 
 
-for f in (conv, attn, lin):
+# round 2: the epilogue-bound K = 320 consumers of a folded LayerNorm (FF1 GEGLU 2560 x 320, spatial q/k/v 1536 x 320), fed by
+# a producer that emits the row statistics
+from aniportrait_b200.models.blocks import fold_layer_norm  # noqa: E402
+
+gam, bet = torch.ones(320, device=dev), torch.zeros(320, device=dev)
+wg1, bg1 = fold_layer_norm(torch.randn(2560, 320, device=dev) * 0.05, torch.zeros(2560, device=dev), gam, bet)
+wg1, bg1 = ops.interleave_geglu(wg1, bg1)
+wq, bq = fold_layer_norm(torch.randn(1536, 320, device=dev) * 0.05, None, gam, bet)
+_, rs = ops.gemm(a, w2, bias=b, residual=res, out=o2, row_stats=True)
+og = torch.empty(131072, 1280, device=dev, dtype=torch.float16)
+oq = torch.empty(131072, 1536, device=dev, dtype=torch.float16)
+
+
+def geglu():
+    ops.gemm(o2, wg1, bias=bg1, geglu=True, out=og, ln=ops.LNFold(rs, 1e-5))
+
+
+def qkv():
+    ops.gemm(o2, wq, bias=bq, out=oq, ln=ops.LNFold(rs, 1e-5))
+
+
+for f in (conv, attn, lin, geglu, qkv):
     f()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
@@ -49,6 +70,10 @@ if which in ("all", "attn"):
     attn()
 if which in ("all", "lin"):
     lin()
+if which in ("all", "geglu"):
+    geglu()
+if which in ("all", "qkv"):
+    qkv()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("done")
