@@ -58,6 +58,7 @@ struct GemmParams {
   // TMA epilogue (per-warp 32-row x 32-column boxes staged in 64B-swizzled shared memory)
   int tma_epi;             // 1: outputs leave through TMA stores, the residual arrives through TMA loads
   int sub_w, sub_h, sub_n; // conv modes: geometry of a warp's 32-row sub-box
+  int epi_double;          // double-buffered output staging when there is no residual (AP_GEMM_EPI_DOUBLE=0 disables: A/B)
   int debug;               // AP_GEMM_DEBUG: 1 = skip TMA loads (MMA pace), 2 = skip MMAs (TMA pace), 3 / 4 = skip every other
                            // B / A load (traffic sensitivity); results are garbage
   // ---- statistics fused into the epilogue (TMA epilogue only) --------------------------------------------------------
@@ -331,8 +332,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
       constexpr int ACC_PER_CHUNK = (EPI == EPI_GEGLU) ? 64 : 32;
       constexpr int NCHUNK = BN / ACC_PER_CHUNK;
       const int ew = warp - 2;
-      uint8_t* obuf = smem_epi + ew * 4096;
-      uint8_t* rbuf = obuf + 2048;
+      uint8_t* obuf0 = smem_epi + ew * 4096;
+      uint8_t* rbuf = obuf0 + 2048;
+      // Without a residual the second 2 KB box of this warp is free: the output staging is then DOUBLE-buffered, so a chunk's
+      // fp16 tile can be written while the TMA store of the previous chunk is still reading the other box (the K = 320
+      // consumers are latency-bound in the epilogue — ncu: issue 28 % / 54 % active, tensor 45 % / 52 % — and every chunk used
+      // to wait for the previous store to drain).
+      uint32_t ochunk = 0;
       uint64_t* rbar = &res_bar[ew];
       uint32_t rphase = 0;
       const bool has_res = (EPI == EPI_LINEAR) && p.residual != nullptr;
@@ -479,8 +485,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
               }
             }
           }
-          // the previous TMA store out of obuf must have finished reading it
-          if (lane == 0) tma_store_wait_read<0>();
+          // the TMA store that last read the staging box we are about to overwrite must have finished reading it
+          const bool dbl = !has_res && p.epi_double;
+          uint8_t* obuf = (dbl && (ochunk & 1)) ? rbuf : obuf0;
+          ++ochunk;
+          if (lane == 0) {
+            if (dbl) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
           __syncwarp();
           if (want_stats && !row_ok) {   // rows past the end of the tensor are clipped by the store; keep them out of the sums
 #pragma unroll
@@ -797,6 +809,8 @@ static int make_weight_map(CUtensorMap* tm, const void* w, int N, long long K, i
 // Validates and copies the optional epilogue extensions into the kernel parameters (after tma_epi / tile counts are known).
 static int apply_ext(GemmParams& p, const ap_epilogue_ext* ext, int epi, long long m_pad, int k_ln) {
   p.bias_ld = p.N;
+  static const int epi_double = getenv("AP_GEMM_EPI_DOUBLE") ? atoi(getenv("AP_GEMM_EPI_DOUBLE")) : 1;
+  p.epi_double = epi_double;
   if (ext == nullptr) return AP_OK;
   if (ext->bias_ld > 0) p.bias_ld = ext->bias_ld;
   const bool any = ext->row_stat_out || ext->col_stat_out || ext->ln_rstd;

@@ -39,11 +39,6 @@ def pack_conv3x3_weight(w: torch.Tensor, cin_pad_to: int = 64, cout_pad_to: int 
     return wp.reshape(cout_p, 9 * cin_p).contiguous()
 
 
-def pack_conv3x3_weight_two_source(w: torch.Tensor, c1: int) -> torch.Tensor:
-    """Conv over cat([x1 (c1 ch), x2]) -> same layout; channel order inside a tap is already [x1, x2]."""
-    return pack_conv3x3_weight(w)
-
-
 def interleave_geglu(w: torch.Tensor, b: torch.Tensor | None):
     """FeedForward.net.0.proj weight [8C, C] (value half then gate half) -> rows interleaved in blocks of 16:
     [v0..15, g0..15, v16..31, g16..31, ...] so that a 32-column accumulator chunk holds matching value/gate pairs."""

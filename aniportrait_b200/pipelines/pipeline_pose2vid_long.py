@@ -104,10 +104,13 @@ class Pose2VideoPipeline:
         self._progress_bar_config = kwargs
 
     def enable_vae_slicing(self):
-        pass
+        """Reference surface (pipeline_pose2vid_long.py:82-86). Slicing trades speed for activation memory in diffusers' VAE;
+        decode_latents_device() already bounds the decoder's activations by decoding `frame_batch` frames per call, so the
+        switch only selects that bound: enabled = one frame per call (the reference's sliced behaviour)."""
+        self.vae_frame_batch = 1
 
     def disable_vae_slicing(self):
-        pass
+        self.vae_frame_batch = 8
 
     # -------------------------------------------------------------------------------------------- stages
     def prepare_latents(self, batch_size, num_channels_latents, width, height, video_length, dtype, device, generator,
@@ -124,9 +127,10 @@ class Pose2VideoPipeline:
         return latents * self.scheduler.init_noise_sigma
 
     @torch.no_grad()
-    def decode_latents_device(self, latents: torch.Tensor, frame_batch: int = 8):
+    def decode_latents_device(self, latents: torch.Tensor, frame_batch: int = None):
         """latents [1, 4, F, h, w] -> device tensor [1, 3, F, H, W] in [0, 1] (reference :113-123, batched)."""
         video_length = latents.shape[2]
+        frame_batch = frame_batch or getattr(self, "vae_frame_batch", 8)
         z = (1 / 0.18215 * latents).permute(0, 2, 1, 3, 4).reshape(-1, *latents.shape[1:2], *latents.shape[3:])
         frames = []
         for i in range(0, z.shape[0], frame_batch):

@@ -56,11 +56,11 @@ def geglu():
     ops.gemm(o2, wg1, bias=bg1, geglu=True, out=og, ln=ops.LNFold(rs, 1e-5))
 
 
-def qkv():
+def qkv_fold():
     ops.gemm(o2, wq, bias=bq, out=oq, ln=ops.LNFold(rs, 1e-5))
 
 
-for f in (conv, attn, lin, geglu, qkv):
+for f in (conv, attn, lin, geglu, qkv_fold):
     f()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
@@ -73,7 +73,7 @@ if which in ("all", "lin"):
 if which in ("all", "geglu"):
     geglu()
 if which in ("all", "qkv"):
-    qkv()
+    qkv_fold()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("done")
