@@ -49,11 +49,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -907,8 +902,9 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint32_t g = 0, uc = 0;
     uint32_t sr[BN];
     // (Round 2: delaying the softmax warps of every second CTA of an SM by 400..1400 clocks, and halving the row-maximum
-    // instructions with FMNMX3, both left the launch at 2.22 ms: the phases without exponentials are already hidden and the
-    // two co-resident CTAs are not phase-locked; profiles/r02_summary.md.)
+    // instructions with FMNMX3, both left the launch at 2.22 ms; eight softmax warps per CTA (two per TMEM lane quarter, each
+    // owning half of a key tile's columns, row maxima exchanged through shared memory) measured 2.52 ms. The variants were
+    // removed after the measurements: profiles/r02_summary.md.)
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
       int frame, head, m_tile, T;
       decode(unit, frame, head, m_tile, T);
@@ -1027,303 +1023,6 @@ static int launch_attention5(const CUtensorMap* maps, const AttnParams& p, cudaS
   return AP_OK;
 }
 
-// ============================================================================================================
-// v6 = v5 with EIGHT softmax warps per CTA (two per TMEM lane quarter, each owning half of a key tile's columns): four softmax
-// warps per SM sub-partition. Opt-in (AP_ATTENTION_V6=1) until measured against v5.
-// ============================================================================================================
-__global__ void __launch_bounds__(320, 2)
-attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBK,
-                  const __grid_constant__ CUtensorMap tmBV, const AttnParams p) {
-  using Cfg = Attn5Cfg;
-  constexpr int ST = Cfg::STAGES, BN = Cfg::BN, DPAD = Cfg::DPAD;
-  griddep_launch_dependents();   // PDL (ap_host.h::launch_pdl)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_kv = smem_q + Cfg::Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ST * Cfg::KV_STAGE);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;            // [ST]
-  uint64_t* v_full = k_full + ST;         // [ST]
-  uint64_t* kv_empty = v_full + ST;       // [ST]
-  uint64_t* s_full = kv_empty + ST;       // [2] per S buffer
-  uint64_t* p_full = s_full + 2;          // [2] per S buffer
-  uint64_t* pv_done = p_full + 2;         // every P.V (rescale path only)
-  uint64_t* o_done = pv_done + 1;         // last P.V of a unit
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
-  // exchange buffers of the two softmax warps that share a TMEM lane quarter (each owns 48 of the 96 key columns of a tile):
-  // row-maximum partials, double-buffered by key-tile parity, and the row-sum partials at the end of a unit
-  float* xmax = reinterpret_cast<float*>(bars + 32);     // [2 parity][2 halves][128 rows]
-  float* xsum = xmax + 2 * 2 * 128;                      // [2 halves][128 rows]
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&p_full[b], 8);
-    }
-    mbar_init(pv_done, 1);
-    mbar_init(o_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  griddep_wait();   // PDL: Q/K/V come from the previous kernel
-
-  const int own_tiles = (p.tokens + BN - 1) / BN;
-  const int bank_tiles = (p.bank_tokens + BN - 1) / BN;
-  const int units_per_frame = p.heads * p.m_tiles;
-
-  auto decode = [&](int unit, int& frame, int& head, int& m_tile, int& T) {
-    const int fk = unit / units_per_frame;
-    const int rem = unit % units_per_frame;
-    frame = (fk + p.first_bank_frame) % p.n_frames;
-    head = rem / p.m_tiles;
-    m_tile = rem % p.m_tiles;
-    const bool has_bank = p.bank_tokens > 0 && frame >= p.first_bank_frame;
-    T = own_tiles + (has_bank ? bank_tiles : 0);
-  };
-
-  if (warp == 0) {
-    // ---------------------------------------------------------------------------- TMA producer
-    uint32_t g = 0, uc = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
-      int frame, head, m_tile, T;
-      decode(unit, frame, head, m_tile, T);
-      mbar_wait(q_empty, (uc & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-        tma_load_2d(&tmQ, q_full, smem_q, head * DPAD, frame * p.tokens + m_tile * 128);
-      }
-      __syncwarp();
-      const int bank_idx = (frame - p.first_bank_frame) / p.frames_per_bank;
-      for (int j = 0; j < T; ++j, ++g) {
-        const int stage = g % ST;
-        mbar_wait(&kv_empty[stage], ((g / ST) & 1) ^ 1);
-        if (elect_one()) {
-          const bool own = j < own_tiles;
-          const CUtensorMap* mk = own ? &tmK : &tmBK;
-          const CUtensorMap* mv = own ? &tmV : &tmBV;
-          const int row = own ? frame * p.tokens + j * BN : bank_idx * p.bank_tokens + (j - own_tiles) * BN;
-          uint8_t* kd = smem_kv + stage * Cfg::KV_STAGE;
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::K_BYTES);
-          tma_load_2d(mk, &k_full[stage], kd, head * DPAD, row);
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::K_BYTES);
-          tma_load_2d(mv, &v_full[stage], kd + Cfg::K_BYTES, head * DPAD, row);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------------------- MMA issuer (warp-uniform, elected lane)
-    constexpr uint32_t idesc_qk = umma_idesc_f16(128, BN, 0, 0);
-    // d = 40 in a 64-wide slot: the zero padding is not multiplied (3 of 4 k-steps for Q.K^T, N = 48 for P.V)
-    const int k_steps = (p.head_dim + 15) >> 4;
-    const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)k_steps * 16, 0, 1);
-    const uint32_t qa = smem_u32(smem_q);
-    uint32_t g = 0, uc = 0;
-    auto issue_qk = [&](uint32_t gi, bool last_of_unit) {
-      const int stage = gi % ST;
-      mbar_wait(&k_full[stage], (gi / ST) & 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + ((gi & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0);
-      const uint32_t ka = smem_u32(smem_kv + stage * Cfg::KV_STAGE);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < DPAD / 16; ++kk)
-          if (kk < k_steps)
-            umma_f16_ss(d_tmem, umma_desc_k_sw128(qa + kk * 32), umma_desc_k_sw128(ka + kk * 32), idesc_qk, kk != 0);
-        umma_commit(&s_full[gi & 1]);
-        if (last_of_unit) umma_commit(q_empty);
-      }
-      __syncwarp();
-    };
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
-      int frame, head, m_tile, T;
-      decode(unit, frame, head, m_tile, T);
-      mbar_wait(q_full, uc & 1);
-      for (int j = 0; j < T; ++j, ++g) {
-        // S buffer (g+1)&1 last held P(g-1), consumed by P.V(g-1) which was issued earlier (tcgen05.mma runs in order)
-        if (j == 0) issue_qk(g, T == 1);
-        if (j + 1 < T) issue_qk(g + 1, j + 2 == T);
-        const int stage = g % ST;
-        mbar_wait(&p_full[g & 1], (g >> 1) & 1);
-        mbar_wait(&v_full[stage], (g / ST) & 1);
-        tc_fence_after();
-        const uint32_t a_tmem = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0);   // P aliases its S buffer
-        const uint32_t va = smem_u32(smem_kv + stage * Cfg::KV_STAGE + Cfg::K_BYTES);
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk)
-            umma_f16_ts(tmem_base + Cfg::TMEM_O, a_tmem + kk * 8, umma_desc_mn_sw128(va + kk * (16 * 128), BN * 128),
-                        idesc_pv, (j | kk) != 0);
-          umma_commit(&kv_empty[stage]);
-          umma_commit(pv_done);
-          if (j + 1 == T) umma_commit(o_done);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------------------- softmax + epilogue: 8 warps, two per TMEM
-    // lane quarter; warp (quarter, half) owns key columns [48 half, 48 half + 48) of every 96-key tile for its 32 query rows.
-    // Four softmax warps per SM sub-partition (2 CTAs x 2) instead of two: the MUFU pipe no longer idles while a warp sits in
-    // its tcgen05.ld / row-max / tcgen05.st phases. Costs: one 64-thread named barrier per key tile (row-maximum exchange).
-    constexpr int HC = BN / 2;                       // 48 key columns per warp
-    const int lane_group = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = lane_group * 32 + lane;
-    const uint32_t t_lane = static_cast<uint32_t>(lane_group * 32) << 16;
-    const uint32_t t_o = tmem_base + Cfg::TMEM_O + t_lane;
-    const uint32_t pair_bar = 1 + lane_group;        // named barrier of this quarter's warp pair
-    uint32_t g = 0, uc = 0;
-    uint32_t sr[HC];
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++uc) {
-      int frame, head, m_tile, T;
-      decode(unit, frame, head, m_tile, T);
-      float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < T; ++j, ++g) {
-        const uint32_t t_s = tmem_base + ((g & 1) ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + t_lane;
-        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-        tc_fence_after();
-        tmem_ld_32x32b_x32(t_s + HC * half, sr);
-        tmem_ld_32x32b_x16(t_s + HC * half + 32, sr + 32);
-        tmem_ld_wait();
-        const bool own = j < own_tiles;
-        const int jj = own ? j : j - own_tiles;
-        const int ntok = own ? p.tokens : p.bank_tokens;
-        const int valid = min(BN, ntok - jj * BN) - HC * half;     // valid columns among this warp's 48
-        if (valid < HC) {
-#pragma unroll
-          for (int i = 0; i < HC; ++i)
-            if (i >= valid) sr[i] = __float_as_uint(-INFINITY);
-        }
-        float mx[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx[i] = fmax3(__uint_as_float(sr[i]), __uint_as_float(sr[8 + i]), __uint_as_float(sr[16 + i]));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx[i] = fmax3(mx[i], __uint_as_float(sr[24 + i]), __uint_as_float(sr[32 + i]));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __uint_as_float(sr[40 + i]));
-        const float hmax = fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
-        float* xm = xmax + (g & 1) * 256;
-        xm[half * 128 + row] = hmax;
-        named_bar_sync(pair_bar, 64);
-        float tmax = fmaxf(hmax, xm[(half ^ 1) * 128 + row]) * p.scale_log2;
-        float alpha = 1.f;
-        bool need = false;
-        if (j == 0) {
-          m_run = tmax;
-        } else if (tmax > m_run + kRescaleThreshold) {
-          alpha = fast_exp2(m_run - tmax);
-          m_run = tmax;
-          need = true;
-        }
-        // both warps of the pair take the same decision only if they vote over the same 32 rows: they do (same quarter)
-        const bool warp_need = __any_sync(0xffffffffu, need);
-        l_run *= alpha;
-        if (warp_need) {   // rare: this warp rescales its half of O (32 of the 64 columns)
-          mbar_wait(pv_done, (g - 1) & 1);
-          tc_fence_after();
-          uint32_t orr[32];
-          tmem_ld_32x32b_x32(t_o + 32 * half, orr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-          tmem_st_32x32b_x32(t_o + 32 * half, orr);
-        }
-        uint32_t pk[HC / 2];
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < HC; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, -m_run));
-          ls[(i >> 1) & 3] += p0 + p1;
-          const __half2 h = __floats2half2_rn(p0, p1);
-          pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-        // this warp's 24 packed P columns -> TMEM columns [24 half, 24 half + 24) of the S buffer (all of its scores were
-        // read by BOTH warps before the barrier above, so overwriting any S column is safe)
-        tmem_st_32x32b_x16(t_s + (HC / 2) * half, pk);
-        tmem_st_32x32b_x8(t_s + (HC / 2) * half + 16, pk + 16);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g & 1]);
-      }
-      // ------------------------------------------------------------------ epilogue: each warp normalises 32 of the O columns
-      xsum[half * 128 + row] = l_run;
-      mbar_wait(o_done, uc & 1);
-      tc_fence_after();
-      named_bar_sync(pair_bar, 64);
-      const float inv_l = 1.f / (l_run + xsum[(half ^ 1) * 128 + row]);
-      const int q_idx = m_tile * 128 + row;
-      const bool row_ok = q_idx < p.tokens;
-      __half* dst = p.out + ((long long)frame * p.tokens + q_idx) * p.ldo + head * p.head_dim;
-      if (half * 32 < p.head_dim) {
-        uint32_t orr[32];
-        tmem_ld_32x32b_x32(t_o + half * 32, orr);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (half * 32 + q * 8 < p.head_dim) {
-              __half2 o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = __floats2half2_rn(__uint_as_float(orr[q * 8 + 2 * i]) * inv_l,
-                                         __uint_as_float(orr[q * 8 + 2 * i + 1]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + half * 32 + q * 8) = *reinterpret_cast<uint4*>(o);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(pair_bar, 64);      // xsum may be overwritten by the next unit only after both warps have read it
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-  }
-}
-
-static int launch_attention6(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
-  using Cfg = Attn5Cfg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(attention6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES + 4096));
-    attr_set = true;
-  }
-  const int max_ctas = 2 * num_sms();
-  const int grid = p.num_units < max_ctas ? p.num_units : max_ctas;
-  AP_LAUNCH((attention6_kernel), grid, 320, Cfg::SMEM_BYTES + 4096, stream, maps[0], maps[1], maps[2], maps[3], maps[4], p);
-  AP_CHECK_CUDA(cudaGetLastError());
-  return AP_OK;
-}
-
 template <int DPAD, int BN>
 static int launch_attention(const CUtensorMap* maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = AttnCfg<DPAD, BN>;
@@ -1409,8 +1108,6 @@ extern "C" int ap_attention_f16(const void* q, const void* k, const void* v, lon
     maps[4] = maps[2];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool use_v6 = getenv("AP_ATTENTION_V6") != nullptr && atoi(getenv("AP_ATTENTION_V6")) != 0;
-  if (use_v5 && use_v6) return launch_attention6(maps, p, st);
   if (use_v5) return launch_attention5(maps, p, st);
   if (use_v3) return dpad == 64 ? launch_attention3<64, 128>(maps, p, st) : launch_attention3<128, 128>(maps, p, st);
   if (dpad == 64) return launch_attention<64, 128>(maps, p, st);
