@@ -58,11 +58,16 @@ class RunCtx:
     """Per-forward state threaded through the blocks."""
 
     def __init__(self, batch: int, frames: int, temb_act: torch.Tensor | None, ehs: torch.Tensor | None,
-                 ehs_key=None, ref_branch=None, emit_stats: bool = True, temb_bias=None):
+                 ehs_key=None, ref_branch=None, emit_stats: bool = True, temb_bias=None, group=None):
         # ref_branch: None = the reference's layout (both CFG branches in the batch when the reader was built with
         # do_classifier_free_guidance); "uncond" / "cond" = this call carries ONE branch of a CFG reader (multi-GPU
         # (window, branch) work units): uncond never reads the bank, cond reads the conditional bank for every frame
         self.ref_branch = ref_branch
+        # group = (n_uncond, n_cond): the batch elements are WINDOWS OF ONE VIDEO, the first n_uncond unconditional, the rest
+        # conditional (sharded mode: all units of a rank in one call -> larger GEMMs, fewer wave-quantisation losses than one
+        # batch-1 call per unit). Unconditional elements never read the bank, every conditional element reads the video's
+        # conditional bank.
+        self.group = group
         self.B = batch              # CFG branches x videos
         self.F = frames             # frames per batch element (1 for the 2-D ReferenceNet)
         self.temb_act = temb_act    # SiLU(time embedding) [B, 1280] fp16
@@ -304,7 +309,7 @@ class BasicTransformerBlock(nn.Module):
             return compute(), 1
         # (video, CFG branch layout, batch, packed weights): a video needs at most 3 entries (both branches together,
         # uncond alone, cond alone)
-        key = (ctx.ehs_key, ctx.ref_branch, ehs.shape[0], id(pk))
+        key = (ctx.ehs_key, ctx.ref_branch, ctx.group, ehs.shape[0], id(pk))
         cache = self._attn2_const if isinstance(self._attn2_const, dict) else {}
         if key not in cache:
             if len(cache) >= 4:
@@ -351,10 +356,18 @@ class BasicTransformerBlock(nn.Module):
             qkv = ops.gemm(n1, pk["wqkv"])
         q, k, v = qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:]
         kw = {}
-        if self._ref_mode == "read" and len(self.bank) > 0 and ctx.ref_branch != "uncond":
+        if self._ref_mode == "read" and len(self.bank) > 0 and ctx.ref_branch != "uncond" and \
+                not (ctx.group is not None and ctx.group[1] == 0):
             kv, nb = self._bank_projection(pk, tokens)
             bank_tokens = self.bank[0].shape[1]
-            if self._ref_cfg and ctx.ref_branch == "cond":
+            if self._ref_cfg and ctx.group is not None:
+                # windows of one video: elements [0, n_uncond) skip the bank, all the others read the conditional bank
+                n_uncond, n_cond = ctx.group
+                nbh = nb // 2
+                kw = dict(bank_k=kv[nbh * bank_tokens:, :hp], bank_v=kv[nbh * bank_tokens:, hp:],
+                          bank_tokens=bank_tokens, n_banks=nb - nbh, first_bank_frame=n_uncond * ctx.F,
+                          frames_per_bank=n_cond * ctx.F)
+            elif self._ref_cfg and ctx.ref_branch == "cond":
                 # single-branch call of a CFG reader: every frame reads the bank of the conditional ReferenceNet pass
                 nbh = nb // 2
                 kw = dict(bank_k=kv[nbh * bank_tokens:, :hp], bank_v=kv[nbh * bank_tokens:, hp:],

@@ -221,7 +221,7 @@ class UNet3DConditionModel(ModelBase):
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward_nhwc(self, x: torch.Tensor, batch: int, frames: int, timestep, encoder_hidden_states,
-                     pose_nhwc=None, ref_branch=None, ehs_key=None) -> torch.Tensor:
+                     pose_nhwc=None, ref_branch=None, ehs_key=None, group=None) -> torch.Tensor:
         """x: [(batch frames), H, W, 64] fp16 (4 latent channels zero padded to 64). pose_nhwc: 5 maps, each
         [(batch frames) | frames, h, w, C] (a [frames,...] map is shared by all CFG branches).
         Returns [(batch frames), H, W, out_channels] fp16."""
@@ -243,7 +243,8 @@ class UNet3DConditionModel(ModelBase):
         if pk["temb"] is not None:
             tb = ops.gemm(temb_act, pk["temb"]["w"], bias=pk["temb"]["b"], out_f32=True)            # [B, sum of couts] fp32
             temb_bias = {rid: tb[:, off:off + n] for rid, off, n in pk["temb"]["slices"]}
-        ctx = RunCtx(batch, frames, temb_act, ehs, ehs_key=ehs_key, ref_branch=ref_branch, temb_bias=temb_bias)
+        ctx = RunCtx(batch, frames, temb_act, ehs, ehs_key=ehs_key, ref_branch=ref_branch, temb_bias=temb_bias,
+                     group=group)
 
         def add_pose(x, k):
             if pose_nhwc is None:
@@ -272,7 +273,7 @@ class UNet3DConditionModel(ModelBase):
         hn = ops.group_norm(x, pk["gn"], pk["bn"], self.groups, self.eps, True, stats=_cs(x))
         return ops.conv3x3(hn, pk["wo"], self.conv_out.out_channels, bias=pk["bo"])
 
-    def prepare_reference(self, batch: int, frames: int, encoder_hidden_states, ehs_key=None, ref_branch=None):
+    def prepare_reference(self, batch: int, frames: int, encoder_hidden_states, ehs_key=None, ref_branch=None, group=None):
         """Once per video, before the denoising loop: every reader block projects its ReferenceNet bank to K/V and
         evaluates its (query-independent) attn2 constant, so that the per-step forward — typically replayed from a CUDA
         graph — contains none of this step-invariant work."""
@@ -280,7 +281,7 @@ class UNet3DConditionModel(ModelBase):
         ehs = encoder_hidden_states.to(torch.float16).contiguous()
         if ehs_key is None:
             raise ValueError("prepare_reference needs an explicit ehs_key (the identity of this video's conditioning)")
-        ctx = RunCtx(batch, frames, None, ehs, ehs_key=ehs_key, ref_branch=ref_branch)
+        ctx = RunCtx(batch, frames, None, ehs, ehs_key=ehs_key, ref_branch=ref_branch, group=group)
         from .blocks import TemporalTransformer3DModel
         for m in self.modules():
             if isinstance(m, BasicTransformerBlock):

@@ -73,6 +73,10 @@ class Pose2VideoPipeline:
         self.use_cuda_graph = True        # capture every stage of a video geometry once (a _Session), replay afterwards
         self.capture_library_stage = True  # also capture CLIP + VAE-encode (falls back to eager if not capturable)
         self.max_sessions = 2
+        # sharded modes: a rank's (window, branch) units are batched into UNet calls of up to `group_units` elements
+        # (unconditional windows first), instead of one batch-1 / batch-2 call per unit: larger GEMMs, fewer
+        # wave-quantisation losses. 0 = one call per unit.
+        self.group_units = 4
         self._sessions = {}
         self._side_stream = None
 
@@ -259,7 +263,12 @@ class Pose2VideoPipeline:
         for idx in S.win_idx_long:
             fea = self.pose_guider.forward_nhwc(S.pose_cond.index_select(0, idx))
             S.win_pose.append([f.to(torch.float16).contiguous() for f in fea])
-        branches = {br for _, br in S.units} or {"both"}
+        branches = {br for k, br in S.units if k != "group"} or ({"both"} if not S.groups else set())
+        for G in S.groups:      # batched units: per-group pose features / embeddings (static buffers once captured)
+            n, nu = len(G["elems"]), G["n_uncond"]
+            G["pose"] = [torch.cat([S.win_pose[k][m] for k, _ in G["elems"]], 0).contiguous() for m in range(5)]
+            G["ehs"] = torch.stack([S.ehs[b] for _, b in G["elems"]], 0).contiguous()            # [n, 1, 768]
+            self.denoising_unet.prepare_reference(n, S.frames0, G["ehs"], ehs_key=S.video_key, group=(nu, n - nu))
         if "both" in branches:
             self.denoising_unet.prepare_reference(S.dup, S.frames0, S.ehs, ehs_key=S.video_key)
         for b, br in enumerate(("uncond", "cond")):       # single-branch (batch-1) units of a CFG reader
@@ -273,9 +282,38 @@ class Pose2VideoPipeline:
                                                 ehs_key=S.video_key)
         ops.scatter_accumulate(pred, idx, S.acc)
 
+    def _plan_groups(self, S, units):
+        """Sharded CFG sessions: the rank's units as batched calls. Elements (window, branch) in unit order, cut into groups
+        of at most `group_units`, each ordered unconditional-first (the layout the attention kernel needs: frames before
+        first_bank_frame skip the bank). Returns the execution list [("group", i)] and fills S.groups (static tensors only;
+        the pose / embedding tensors of a group are built by _stage_reference_read)."""
+        elems = []
+        for k, br in units:
+            elems += [(k, 0), (k, 1)] if br == "both" else [(k, 0 if br == "uncond" else 1)]
+        S.groups = []
+        for i in range(0, len(elems), self.group_units):
+            g = sorted(elems[i:i + self.group_units], key=lambda e: e[1])       # stable: uncond (0) first
+            S.groups.append(dict(elems=g, n_uncond=sum(1 for _, b in g if b == 0),
+                                 idx_all=torch.cat([S.win_idx[k] for k, _ in g]).contiguous(), pose=None, ehs=None))
+        return [("group", i) for i in range(len(S.groups))]
+
+    def _group_step(self, S, gi):
+        """All elements of group gi in ONE UNet call: batch = windows of this video, unconditional ones first."""
+        G = S.groups[gi]
+        n, nu = len(G["elems"]), G["n_uncond"]
+        F = S.win_idx[G["elems"][0][0]].numel()
+        x = ops.gather_window(S.lat, G["idx_all"], 1, 64)
+        pred = self.denoising_unet.forward_nhwc(x, n, F, S.t_dev, G["ehs"], G["pose"], ehs_key=S.video_key,
+                                                group=(nu, n - nu))
+        for e, (k, b) in enumerate(G["elems"]):
+            ops.scatter_accumulate(pred[e * F:(e + 1) * F], S.win_idx[k], S.acc[b:b + 1])
+
     def _unit_step(self, S, k, branch):
         """One (window, CFG-branch) work unit. "both" = the reference's layout (both branches in one batch); "uncond" /
-        "cond" = a batch-1 UNet call for one branch (sharded mode only), accumulated into that branch's plane."""
+        "cond" = a batch-1 UNet call for one branch (sharded mode only), accumulated into that branch's plane;
+        ("group", i) = a batched call over several units of this rank (_plan_groups)."""
+        if k == "group":
+            return self._group_step(S, branch)
         if branch == "both":
             return self._window_step(S, k)
         idx = S.win_idx[k]
@@ -333,6 +371,9 @@ class Pose2VideoPipeline:
         S.n_embed = S.n_reference = S.n_write = 0
         S.n_units = []
         S.bank_shapes = S.bank_flat = None
+        S.groups = []
+        if shard and dup == 2 and self.group_units and units:
+            S.units = self._plan_groups(S, units)
         return S
 
     def _capture(self, fn, pool=None):
@@ -495,7 +536,8 @@ class Pose2VideoPipeline:
         static = bool(self.use_cuda_graph)
 
         if static:
-            key = (L, h, w, dup, tuple(tuple(wd) for wd in my_windows), tuple(units), shard, rank, world, clip_is_embed,
+            key = (L, h, w, dup, tuple(tuple(wd) for wd in my_windows), tuple(units), shard, rank, world,
+                   self.group_units if shard else 0, clip_is_embed,
                    tuple(clip_in.shape), tuple(ref_image_tensor.shape), tuple(pose_cond.shape),
                    self._weights_fingerprint())
             S = self._sessions.get(key)
@@ -539,7 +581,7 @@ class Pose2VideoPipeline:
                         g.replay()
                         ops._count(n)
                 else:
-                    for k, branch in units:
+                    for k, branch in S.units:
                         self._unit_step(S, k, branch)
                 if shard:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

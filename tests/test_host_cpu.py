@@ -397,3 +397,35 @@ def test_vae_quant_conv_folding_algebra():
     z1 = torch.cat([z, torch.ones(2, 1, 6, 5)], 1)
     got = F.conv2d(z1, w_f, bi[:64], padding=1)
     assert rel_l2(got, ref) < 2e-3
+
+
+def test_unit_groups_cover_every_unit_once_uncond_first():
+    """Sharded mode: a rank's (window, branch) units are batched into UNet calls of <= group_units elements, unconditional
+    windows first inside every group (the attention kernel's bank rule: frames before first_bank_frame skip the bank)."""
+    from aniportrait_b200.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline, _Session
+    from aniportrait_b200.pipelines.sharding import plan_units
+
+    class P(Pose2VideoPipeline):
+        def __init__(self):
+            self.group_units = 4
+    for world in (2, 4, 8):
+        for rank, mine in enumerate(plan_units(11, True, world)):
+            ids = sorted({k for k, _ in mine})
+            units = [(ids.index(k), br) for k, br in mine]
+            S = _Session()
+            S.win_idx = [torch.arange(16, dtype=torch.int32) + 12 * k for k in ids]
+            execs = P()._plan_groups(S, units)
+            assert execs == [("group", i) for i in range(len(S.groups))]
+            seen = []
+            for G in S.groups:
+                assert 1 <= len(G["elems"]) <= 4
+                bs = [b for _, b in G["elems"]]
+                assert bs == sorted(bs) and G["n_uncond"] == bs.count(0)
+                assert G["idx_all"].numel() == 16 * len(G["elems"])
+                for e, (k, b) in enumerate(G["elems"]):
+                    assert torch.equal(G["idx_all"][16 * e:16 * e + 16], S.win_idx[k])
+                seen += G["elems"]
+            want = []
+            for k, br in units:
+                want += [(k, 0), (k, 1)] if br == "both" else [(k, 0 if br == "uncond" else 1)]
+            assert sorted(seen) == sorted(want)

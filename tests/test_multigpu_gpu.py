@@ -40,8 +40,13 @@ def _worker(rank, world, port, q):
     assert torch.equal(pipe.last_latents.float().cpu(), sharded_lat)
     pipe.collect_timings()
     assert pipe.timings.get("bank_broadcast_ms", 0.0) > 0.0 and pipe.timings.get("all_reduce_ms", 0.0) > 0.0
-    pipe(*args, latents=lat0.clone(), dist_mode="window_branches")        # (window, CFG branch) units: 4 units on 2 ranks
-    branch_lat = pipe.last_latents.float().cpu()
+    pipe(*args, latents=lat0.clone(), dist_mode="window_branches")        # (window, CFG branch) units: 4 units on 2 ranks,
+    branch_lat = pipe.last_latents.float().cpu()                          # batched into one UNet call per rank (group_units)
+    pipe.group_units = 0                                                   # the same with one call per unit
+    pipe(*args, latents=lat0.clone(), dist_mode="window_branches")
+    ungrouped_lat = pipe.last_latents.float().cpu()
+    pipe.group_units = 4
+    assert float((ungrouped_lat - branch_lat).norm() / branch_lat.norm()) < 5e-3
     # clips mode: every rank runs its own clip end to end (rank-dependent noise), no data-path collective
     lat_r = torch.randn((1, 4, L, P["size"] // 8, P["size"] // 8), generator=torch.manual_seed(100 + rank)).to(torch.float16)
     clips = pipe(*args, latents=lat_r.clone(), dist_mode="clips").videos
