@@ -150,3 +150,46 @@ def test_vae_encode():
     assert ours.shape == (2, 8, 8, 6)
     assert rel_l2(ours[:, :4], dist.mean) < 1e-5
     assert rel_l2(ours, torch.cat([dist.mean, dist.logvar], 1)) < 1e-5
+
+
+def test_denoise_loop_against_the_reference_pipeline_golden():
+    """The oracle's whole denoising loop (windows with wrap-around, in-loop PoseGuider on the CFG-duplicated batch, overlap
+    accumulation, CFG, DDIM) + VAE decode against the committed output of the UNMODIFIED reference pipeline
+    (tests/golden/pipeline_small.pt: L=20 -> two overlapping 16-frame windows, 3 steps). The host-side preparation below restates
+    pipeline_pose2vid_long.py:373-447 with the (shim) library objects the reference itself uses. This is the checker the GPU
+    tests use for the single-window / image pipelines, so it is pinned at pipeline level too."""
+    gold_path = os.path.join(ROOT, "tests", "golden", "pipeline_small.pt")
+    if not os.path.exists(gold_path):
+        pytest.skip("golden missing")
+    ref_import.activate()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden as MG
+    from diffusers import AutoencoderKL
+    from diffusers.image_processor import VaeImageProcessor
+    from transformers import CLIPImageProcessor
+    gold = torch.load(gold_path)
+    P = gold["params"]
+    seeds = P["seeds"]
+    sd3 = _load(ref_import.build_unet3d(P["chans"]), seeds["unet3d"])
+    sd2 = _load(ref_import.build_unet2d(P["chans"]), seeds["unet2d"])
+    sdp = _load(ref_import.build_pose_guider(P["chans"][0]), seeds["pose"])
+    vae = AutoencoderKL(block_out_channels=P["vae_chans"])
+    sdv = _load(vae, seeds["vae"])
+    clip = MG.small_clip_encoder(seeds["clip"])
+    size, L = P["size"], P["L"]
+    ref_image, poses, _ = MG.pipeline_inputs(size, L, seeds["inputs"])
+    with torch.no_grad():
+        clip_px = CLIPImageProcessor().preprocess(ref_image.resize((224, 224)), return_tensors="pt").pixel_values
+        clip_embed = clip(clip_px).image_embeds
+        ref_t = VaeImageProcessor(vae_scale_factor=8, do_convert_rgb=True).preprocess(ref_image, height=size, width=size)
+        ref_lat = vae.encode(ref_t).latent_dist.mean * 0.18215
+        cond = VaeImageProcessor(vae_scale_factor=8, do_convert_rgb=True, do_normalize=True)
+        pose_cond = torch.cat([cond.preprocess(p, height=size, width=size) for p in poses], 0)      # [L, 3, H, W]
+        pose_cond = pose_cond.permute(1, 0, 2, 3).unsqueeze(0)
+        lat0 = torch.randn((1, 4, L, size // 8, size // 8), generator=torch.manual_seed(seeds["latents"]))
+        out = OF.denoise_loop(sd3, sd2, sdp, lat0, ref_lat, clip_embed, pose_cond, P["steps"], guidance=P["guidance"],
+                              c=dict(OF.SD15, block_out_channels=tuple(P["chans"])))
+        frames = [0, 7, L - 1]
+        video = (OF.vae_decode(sdv, out[0, :, frames].permute(1, 0, 2, 3) / 0.18215) / 2 + 0.5).clamp(0, 1)
+    assert rel_l2(out, gold["final_latents"]) < 1e-4
+    assert rel_l2(video.permute(1, 0, 2, 3).unsqueeze(0), gold["video_frames"].float()) < 2e-3     # the fixture stores fp16
