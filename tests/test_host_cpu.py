@@ -143,7 +143,7 @@ def _gloo_worker(rank, world, port, L, out_q):
     dist.all_reduce(acc)
     out = combine(acc, inv, 3.5)
     if rank == 0:
-        out_q.put(out)
+        out_q.put(out.numpy())      # by value: a tensor handle would die with this process
     dist.destroy_process_group()
 
 
@@ -171,7 +171,7 @@ def test_window_sharding_world2_gloo():
         pred = torch.stack([torch.sin(x[0] * 1.3), torch.cos(x[0] * 0.7)]) + x.mean(dim=2, keepdim=True)
         accumulate(acc, pred.permute(0, 2, 1, 3, 4), wd)
     ref = combine(acc, inv, 3.5)
-    assert torch.allclose(got, ref, atol=1e-5)
+    assert torch.allclose(torch.from_numpy(got), ref, atol=1e-5)
 
 
 def test_plan_units_covers_every_window_branch_once_and_balances():
@@ -429,3 +429,70 @@ def test_unit_groups_cover_every_unit_once_uncond_first():
             for k, br in units:
                 want += [(k, 0), (k, 1)] if br == "both" else [(k, 0 if br == "uncond" else 1)]
             assert sorted(seen) == sorted(want)
+
+
+def _gloo_bank_worker(rank, world, port, out_q):
+    """Bank exchange protocol of the sharded sessions on CPU tensors: shape handshake (once per session), rank 0 packs its
+    banks into ONE flat buffer, one broadcast, every rank's writer blocks end up with views of it."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from aniportrait_b200.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline, _Session
+
+    class Blk:
+        def __init__(self):
+            self.bank = []
+
+    class Writer:
+        def __init__(self, mods):
+            self.unet, self.mods = None, mods
+
+        def _modules(self, unet):
+            return self.mods
+
+    class P(Pose2VideoPipeline):
+        def __init__(self):
+            pass
+    shapes = [(2, 16, 256), (2, 16, 256), (2, 64, 128), (2, 256, 64)]
+    mods = [Blk() for _ in shapes]
+    if rank == 0:
+        g = torch.Generator().manual_seed(3)
+        for m, shp in zip(mods, shapes):
+            m.bank = [torch.randn(*shp, generator=g).to(torch.float16)]
+    S = _Session()
+    S.lat = torch.zeros(1)
+    S.writer = Writer(mods)
+    pipe = P()
+    S.bank_shapes = pipe._bank_layout(S)
+    assert S.bank_shapes == shapes
+    S.bank_flat = torch.empty(sum(a * b * c for a, b, c in shapes), dtype=torch.float16)
+    if rank == 0:
+        pipe._pack_banks(S)
+    dist.broadcast(S.bank_flat, 0)
+    pipe._unpack_banks(S)
+    g = torch.Generator().manual_seed(3)
+    same = all(torch.equal(m.bank[0], torch.randn(*shp, generator=g).to(torch.float16)) for m, shp in zip(mods, shapes))
+    lo, hi = S.bank_flat.data_ptr(), S.bank_flat.data_ptr() + S.bank_flat.numel() * 2
+    views = all(lo <= m.bank[0].data_ptr() < hi for m in mods)
+    out_q.put((rank, bool(same), bool(views)))       # plain Python values: no tensor handles cross the process boundary
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bank_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_bank_worker, args=(r, 2, 29547, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        r = q.get(timeout=120)
+        got[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] and got[1][1], "every rank must hold rank 0's banks after the single broadcast"
+    assert got[0][2] and got[1][2], "the banks must be views of the flat broadcast buffer"
