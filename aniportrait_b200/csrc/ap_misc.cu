@@ -512,6 +512,62 @@ __global__ void cfg_ddim_step_kernel(float* __restrict__ acc, const float* __res
   lat[t] = __float2half_rn(sqrt_ap * x0 + sqrt_bp * eps);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Video frames -> packed 8-bit RGB (what the reference does on the host: src/utils/util.py:87-104 save_videos_grid,
+// `(x * 255).numpy().astype(np.uint8)` after an optional `(x + 1) / 2`, on the fp32 copy of the fp16 video). in: fp16
+// [B, 3, F, H, W] addressed through element strides (the decoder's frames live as [F, 3, H, W]); out: [B, F, H, W, 3]
+// bytes. Same fp32 operations in the same order as the host code (no fma contraction) -> bit-identical bytes; out-of-range
+// values saturate (the numpy cast is undefined there), NaN -> 0.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned to_u8(__half h, int rescale) {
+  float x = __half2float(h);
+  if (rescale) x = __fmul_rn(__fadd_rn(x, 1.f), 0.5f);
+  return min(__float2uint_rz(__fmul_rn(x, 255.f)), 255u);   // cvt.rzi.u32.f32 saturates: negative and NaN -> 0
+}
+
+// VEC = 4: one thread packs four neighbouring pixels of a row (three 8-byte loads, three 4-byte stores); VEC = 1: any strides
+template <int VEC>
+__global__ void __launch_bounds__(256)
+pack_frames_u8_kernel(const __half* __restrict__ in, long long sb, long long sc, long long sf, long long sh, long long sw,
+                      int B, int F, int H, int W, int rescale, uint8_t* __restrict__ out) {
+  griddep_launch_dependents();   // PDL: see ap_host.h::launch_pdl
+  griddep_wait();
+  const int Wv = W / VEC;
+  const long long total = (long long)B * F * H * Wv;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; t < total; t += stride) {
+    const int xv = (int)(t % Wv);
+    long long r = t / Wv;
+    const int y = (int)(r % H);
+    r /= H;
+    const int f = (int)(r % F);
+    const int b = (int)(r / F);
+    const __half* src = in + b * sb + f * sf + y * sh;
+    if (VEC == 4) {
+      unsigned px[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src + c * sc + xv * 4);
+        const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
+        px[c][0] = to_u8(__low2half(lo), rescale);
+        px[c][1] = to_u8(__high2half(lo), rescale);
+        px[c][2] = to_u8(__low2half(hi), rescale);
+        px[c][3] = to_u8(__high2half(hi), rescale);
+      }
+      // 12 bytes r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3 (little endian)
+      uint32_t* o = reinterpret_cast<uint32_t*>(out + t * 12);
+      o[0] = px[0][0] | (px[1][0] << 8) | (px[2][0] << 16) | (px[0][1] << 24);
+      o[1] = px[1][1] | (px[2][1] << 8) | (px[0][2] << 16) | (px[1][2] << 24);
+      o[2] = px[2][2] | (px[0][3] << 8) | (px[1][3] << 16) | (px[2][3] << 24);
+    } else {
+      uint8_t* o = out + t * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = (uint8_t)to_u8(src[c * sc + xv * sw], rescale);
+    }
+  }
+}
+
 static inline unsigned grid_for(long long n, int threads, int cap = 148 * 16) {
   long long g = (n + threads - 1) / threads;
   if (g > cap) g = cap;
@@ -663,6 +719,25 @@ extern "C" int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg,
   AP_LAUNCH((cfg_ddim_step_kernel), (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, 
       acc, inv_count, cfg, guidance, c_xx, c_xv, c_ex, c_ev, clip_range, sqrtf(alpha_prev), sqrtf(1.f - alpha_prev),
       (__half*)latents, L, HW);
+  AP_CHECK_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+extern "C" int ap_pack_frames_u8(const void* video, const long long* strides, int B, int F, int H, int W, int rescale,
+                                 void* out, void* stream) {
+  AP_REQUIRE(video && strides && out && B > 0 && F > 0 && H > 0 && W > 0, "pack_frames_u8: bad arguments");
+  const long long sb = strides[0], sc = strides[1], sf = strides[2], sh = strides[3], sw = strides[4];
+  const bool vec = sw == 1 && W % 4 == 0 && sb % 4 == 0 && sc % 4 == 0 && sf % 4 == 0 && sh % 4 == 0 &&
+                   ((uintptr_t)video & 7) == 0 && ((uintptr_t)out & 3) == 0;
+  if (vec) {
+    const long long total = (long long)B * F * H * (W / 4);
+    AP_LAUNCH((pack_frames_u8_kernel<4>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)video, sb, sc,
+              sf, sh, sw, B, F, H, W, rescale, (uint8_t*)out);
+  } else {
+    const long long total = (long long)B * F * H * W;
+    AP_LAUNCH((pack_frames_u8_kernel<1>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)video, sb, sc,
+              sf, sh, sw, B, F, H, W, rescale, (uint8_t*)out);
+  }
   AP_CHECK_CUDA(cudaGetLastError());
   return AP_OK;
 }

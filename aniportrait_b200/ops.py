@@ -574,3 +574,18 @@ def cfg_ddim_step(acc: torch.Tensor, inv_count: torch.Tensor, guidance: float, a
                                      I(PREDICTION_TYPES[prediction_type]), _lib.c_float(clip_range), ptr(latents),
                                      I(L), I(h * w), stream_ptr()), "ap_cfg_ddim_step_f16")
     _count()
+
+
+def pack_frames_u8(video: torch.Tensor, rescale: bool = False) -> torch.Tensor:
+    """video [B, 3, F, H, W] fp16 (any strides, e.g. the decoder's [F, 3, H, W] frames viewed as a video) -> [B, F, H, W, 3]
+    uint8 on the device: the bytes `save_videos_grid` (reference src/utils/util.py:87-104) makes on the host from the fp32
+    copy, `(x * 255).astype(uint8)` after `(x + 1) / 2` if rescale."""
+    _ensure(video)
+    assert video.dim() == 5 and video.shape[1] == 3 and video.dtype == torch.float16, "pack_frames_u8: [B, 3, F, H, W] fp16"
+    B, _, F, H, W = video.shape
+    out = torch.empty(B, F, H, W, 3, dtype=torch.uint8, device=video.device)
+    strides = (_lib.c_longlong * 5)(*video.stride())
+    check(lib().ap_pack_frames_u8(ptr(video), strides, I(B), I(F), I(H), I(W), I(1 if rescale else 0), ptr(out),
+                                  stream_ptr()), "ap_pack_frames_u8")
+    _count()
+    return out

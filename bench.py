@@ -468,6 +468,25 @@ def run_product(args):
     if world > 1:
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
     ms_step, e2e_ms = tt.tolist()
+    # ---- extra leg: the same call returning packed 8-bit frames (output_type="uint8": 1 byte per sample to the host) ----
+    e2e_u8 = None
+    if world == 1:
+        try:
+            def u8_step():
+                return pipe(ref_image, poses, ref_pose, W, H, L, DDIM_STEPS, GUIDANCE, generator=gen, output_type="uint8")
+            u8_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                u8_step()
+            torch.cuda.synchronize()
+            u8_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            e2e_u8 = {"value": round(L / (u8_ms / 1e3), 4), "unit": "frames/s", "ms_per_step": round(u8_ms, 3),
+                      "d2h_bytes_per_step": int(3 * L * H * W),
+                      "note": "same call as `e2e`, frames returned as packed uint8 RGB [1, L, H, W, 3] (what the scripts' "
+                              "save_videos_grid derives on the host); host inputs as in `e2e`"}
+        except Exception as exc:       # an extra: never let it take the headline line down
+            e2e_u8 = {"error": repr(exc)}
     # ---- extra legs (not part of `value`): C1 like-for-like (rank 0, N=1) and the strong-scaling C4 video (every N) ----
     c1 = run_c1(pipe, device) if (world == 1 and args.c1) else None
     strong_c4 = None
@@ -527,6 +546,8 @@ def run_product(args):
                                           how="rel-L2 of the roofline-timed launches' outputs vs a real-fp32 (TF32 off) torch "
                                               "evaluation of the same fp16 inputs on the device"),
         }
+        if e2e_u8 is not None:
+            line["e2e_uint8_frames"] = e2e_u8
         if c1 is not None:
             line["c1"] = c1
         if strong_c4 is not None:

@@ -205,6 +205,16 @@ int ap_scatter_accumulate_f16(const void* pred, int ld, const int* frame_idx, fl
 int ap_cfg_ddim_step_f16(float* acc, const float* inv_count, int cfg, float guidance, float alpha_t, float alpha_prev,
                          int prediction_type, float clip_range, void* latents, int L, int HW, void* stream);
 
+/*
+ * Decoded video -> packed 8-bit RGB frames on the device (reference src/utils/util.py:87-104 save_videos_grid does
+ * `(x * 255).numpy().astype(np.uint8)`, after `(x + 1) / 2` if rescale, on the fp32 host copy that
+ * pipeline_pose2vid_long.py:123-125 makes: 4 bytes per sample over PCIe instead of 1). video: fp16 [B, 3, F, H, W] addressed
+ * through `strides` = element strides of (b, c, f, h, w) (host array of 5); out: [B, F, H, W, 3] bytes. Bit-identical to
+ * the host arithmetic for values in range; out-of-range values saturate, NaN -> 0.
+ */
+int ap_pack_frames_u8(const void* video, const long long* strides, int B, int F, int H, int W, int rescale, void* out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,3 +256,46 @@ def test_scatter_accumulate_repeated_frame_counts_once(cuda_dev):
         ops.scatter_accumulate(pred, idx, acc)
         ref = accumulate(torch.zeros(2, 24, h, w, 4), pred[..., :4].float().cpu().view(2, len(wd), h, w, 4), wd)
         assert torch.equal(acc.cpu(), ref)
+
+
+@pytest.mark.parametrize("rescale", [False, True])
+def test_pack_frames_u8_matches_host_bytes(cuda_dev, rescale):
+    """On-device 8-bit frame packing == the bytes the reference's save_videos_grid makes on the host from the fp32 tensor
+    (src/utils/util.py:94-98: `(x + 1) / 2` if rescale, `(x * 255).numpy().astype(np.uint8)`), bit for bit: every fp16 value
+    of the range (incl. the k/255 neighbourhoods where truncation decides the byte), both the four-pixel and the
+    any-stride kernel, the decoder's [F, 3, H, W] memory order and a plain contiguous video."""
+    import numpy as np
+    from aniportrait_b200 import ops
+
+    def host_bytes(video):          # what the scripts do with pipe(...).videos
+        x = video.float().cpu()
+        if rescale:
+            x = (x + 1.0) / 2.0
+        return (x * 255).numpy().astype(np.uint8).transpose(0, 2, 3, 4, 1)    # b c f h w -> b f h w c
+
+    lo, hi = (-1.0, 1.0) if rescale else (0.0, 1.0)
+    # every finite fp16 bit pattern inside [lo, hi]
+    allh = torch.arange(0, 1 << 16, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    allh = allh[torch.isfinite(allh) & (allh >= lo) & (allh <= hi)]
+    g = torch.Generator().manual_seed(5)
+    for (B, F_, H, W), decoder_order in [((1, 4, 64, 64), True), ((2, 3, 16, 32), False), ((1, 2, 10, 21), True),
+                                         ((1, 3, 8, 20), False)]:
+        n = B * 3 * F_ * H * W
+        vals = allh[torch.randint(0, allh.numel(), (n,), generator=g)]
+        vals[:allh.numel()] = allh[:n] if allh.numel() > n else allh
+        if decoder_order:           # memory [B, F, 3, H, W], handed over as the [B, 3, F, H, W] view the pipeline makes
+            video = vals.view(B, F_, 3, H, W).to(cuda_dev).permute(0, 2, 1, 3, 4)
+        else:
+            video = vals.view(B, 3, F_, H, W).to(cuda_dev)
+        out = ops.pack_frames_u8(video, rescale=rescale)
+        assert out.shape == (B, F_, H, W, 3) and out.dtype == torch.uint8 and out.is_contiguous()
+        assert np.array_equal(out.cpu().numpy(), host_bytes(video)), (B, F_, H, W, decoder_order)
+    # a view with a pixel stride of 2 (takes the any-stride kernel even though W % 4 == 0)
+    wide = allh[torch.randint(0, allh.numel(), (1 * 3 * 2 * 8 * 32,), generator=g)].view(1, 3, 2, 8, 32).to(cuda_dev)
+    sub = wide[..., ::2]
+    assert np.array_equal(ops.pack_frames_u8(sub, rescale=rescale).cpu().numpy(), host_bytes(sub))
+    if not rescale:                 # out of range saturates, NaN -> 0 (the host cast is undefined there)
+        odd = torch.tensor([-0.5, 1.5, float("nan"), 65504.0] * 6, dtype=torch.float16, device=cuda_dev).view(1, 3, 1, 2, 4)
+        got = ops.pack_frames_u8(odd).cpu().view(-1)
+        exp = torch.tensor([0, 255, 0, 255] * 6, dtype=torch.uint8).view(1, 3, 1, 2, 4).permute(0, 2, 3, 4, 1).reshape(-1)
+        assert torch.equal(got, exp)

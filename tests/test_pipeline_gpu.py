@@ -70,6 +70,13 @@ def test_pipeline_no_cfg_single_window(cuda_dev):
     out = pipe(ref_image, poses, ref_pose, P["size"], P["size"], 4, 2, 1.0, generator=torch.manual_seed(1))
     assert out.videos.shape == (1, 3, 4, P["size"], P["size"])
     assert torch.isfinite(out.videos).all()
+    # output_type="uint8": frames packed on the device == the bytes save_videos_grid (reference src/utils/util.py:94-98)
+    # makes on the host from the fp32 tensor of the same run (same seed -> replay of the same session, bit-reproducible)
+    u8 = pipe(ref_image, poses, ref_pose, P["size"], P["size"], 4, 2, 1.0, generator=torch.manual_seed(1),
+              output_type="uint8").videos
+    assert u8.shape == (1, 4, P["size"], P["size"], 3) and u8.dtype == torch.uint8 and not u8.is_cuda
+    host = torch.from_numpy((out.videos * 255).numpy().astype("uint8")).permute(0, 2, 3, 4, 1)
+    assert torch.equal(u8, host)
 
 
 def test_vae_kernel_decode_against_oracle(cuda_dev):
