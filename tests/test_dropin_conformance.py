@@ -29,6 +29,7 @@ from src.pipelines.pipeline_pose2vid_long import Pose2VideoPipeline
 from src.pipelines.pipeline_pose2vid import Pose2VideoPipeline as ShortPipeline
 from src.pipelines.pipeline_pose2img import Pose2ImagePipeline
 from src.pipelines.context import get_context_scheduler
+from src.utils.frame_interpolation import batch_images_interpolation_tool, init_frame_interpolation_model
 
 def sig(fn):
     out = []
@@ -65,6 +66,8 @@ res = {
         "ShortPipeline.__call__": sig(ShortPipeline.__call__),
         "Pose2ImagePipeline.__call__": sig(Pose2ImagePipeline.__call__),
         "context.uniform": sig(get_context_scheduler("uniform")),
+        "batch_images_interpolation_tool": sig(batch_images_interpolation_tool),
+        "init_frame_interpolation_model": sig(init_frame_interpolation_model),
     },
     "keys": {"unet3d": sorted(u3.state_dict().keys()), "unet2d": sorted(u2.state_dict().keys()),
              "pose_guider": sorted(pg.state_dict().keys())},

@@ -496,3 +496,57 @@ def test_bank_exchange_world2_gloo():
         assert p.exitcode == 0
     assert got[0][1] and got[1][1], "every rank must hold rank 0's banks after the single broadcast"
     assert got[0][2] and got[1][2], "the banks must be views of the flat broadcast buffer"
+
+
+class _StandInFilm(torch.nn.Module):
+    """Stand-in for the FILM TorchScript file (absent): same call layout (x0, x1 [n, c, h, w] fp16, dt [n, 1] or [1, 1]),
+    elementwise + shifts only, so that a frame's value cannot depend on the batch it is computed in; leaves [0, 1] on purpose
+    (the wrapper clamps)."""
+
+    def __init__(self):
+        super().__init__()
+        self.anchor = torch.nn.Parameter(torch.zeros(1))       # tells the wrapper which device the network lives on
+
+    def forward(self, x0, x1, dt):
+        t = dt.view(-1, 1, 1, 1).to(x0.dtype)
+        mix = x0 * (1 - t) + x1 * t
+        return mix + 0.3 * torch.sin(7 * torch.roll(x0, 1, -1) - 5 * torch.roll(x1, 1, -2) + 3 * t) - 0.05
+
+
+def test_frame_interpolation_matches_reference_order_and_values(monkeypatch):
+    """N2: the batched `-acc` wrapper returns the frames of the unmodified reference
+    src/utils/frame_interpolation.py:23-69 (one network call per inserted frame and pair, host round trips) — same insertion
+    order, same dt bit patterns, same clamping, same pass-through of the given frames — with `inter_frames` network calls."""
+    import importlib.util
+    ref_path = "/root/reference/src/utils/frame_interpolation.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference checkout not present (authoring container only)")
+    spec = importlib.util.spec_from_file_location("_ref_frame_interpolation", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)     # the reference hard-codes .cuda()
+    from aniportrait_b200.pipelines.frame_interpolation import batch_images_interpolation_tool, insertion_schedule
+
+    class Counting(_StandInFilm):
+        calls = 0
+
+        def forward(self, x0, x1, dt):
+            Counting.calls += 1
+            assert x0.dtype == torch.float16 and dt.dtype == torch.float16
+            return super().forward(x0, x1, dt)
+
+    g = torch.Generator().manual_seed(3)
+    for bs, frames in [(1, 5), (2, 3)]:
+        video = torch.rand((bs, 3, frames, 8, 12), generator=g)              # fp32, not fp16-representable
+        for n in range(1, 6):
+            want = ref.batch_images_interpolation_tool(video, _StandInFilm(), inter_frames=n)
+            Counting.calls = 0
+            got = batch_images_interpolation_tool(video, Counting(), inter_frames=n)
+            assert Counting.calls == n                                        # (frames - 1) * n in the reference
+            assert got.dtype == want.dtype == torch.float32 and got.shape == (bs, 3, (frames - 1) * (n + 1) + 1, 8, 12)
+            assert torch.equal(got, want), (bs, frames, n)
+            assert torch.equal(batch_images_interpolation_tool(video, _StandInFilm(), n, max_pairs_per_call=1), want)
+            assert len(insertion_schedule(n)) == n
+    # the midpoint first, then the quarters: the order for three inserted frames
+    assert [(a, b, c) for a, b, c, _ in insertion_schedule(3)] == [(0, 4, 2), (0, 2, 1), (2, 4, 3)]
+    assert torch.equal(batch_images_interpolation_tool(video, _StandInFilm(), 0), video)
