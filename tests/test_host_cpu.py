@@ -2,6 +2,7 @@
 window scheduler, image pre-processing, weight repacking, state-dict surface) against the oracle; world_size-2 gloo test
 of the window-sharded denoising step."""
 import os
+import subprocess
 import sys
 
 import numpy as np
@@ -550,3 +551,50 @@ def test_frame_interpolation_matches_reference_order_and_values(monkeypatch):
     # the midpoint first, then the quarters: the order for three inserted frames
     assert [(a, b, c) for a, b, c, _ in insertion_schedule(3)] == [(0, 4, 2), (0, 2, 1), (2, 4, 3)]
     assert torch.equal(batch_images_interpolation_tool(video, _StandInFilm(), 0), video)
+
+
+def test_kv_cached_pose_infer_matches_reference_infer(tmp_path):
+    """N3: the incremental (KV-cached, one-key cross-attention precomputed) head-pose decoder returns what the
+    UNMODIFIED reference Audio2PoseModel.infer (src/audio_models/pose_model.py:97-124) computes by re-decoding all tokens at
+    every frame — same module instance, seeded random weights, CPU fp32."""
+    if not os.path.isdir("/root/reference/src/audio_models"):
+        pytest.skip("reference checkout not present (authoring container only)")
+    script = r'''
+import sys, torch
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, sys.argv[2])
+from transformers import Wav2Vec2Config
+cfg = Wav2Vec2Config(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                     conv_dim=(32, 32, 32), conv_stride=(5, 4, 2), conv_kernel=(10, 4, 2), num_feat_extract_layers=3,
+                     num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4)
+cfg._attn_implementation = "eager"        # the reference's wav2vec2 wrapper asks for attention maps
+cfg.save_pretrained(sys.argv[1])
+from src.audio_models.pose_model import Audio2PoseModel
+from aniportrait_b200.audio_models import enable_kv_cache, kv_cached_infer
+worst = 0.0
+for seed, latent, T, only_last in [(0, 64, 37, True), (1, 128, 61, False)]:
+    torch.manual_seed(seed)
+    m = Audio2PoseModel(dict(latent_dim=latent, model_path=sys.argv[1], only_last_fetures=only_last,
+                             from_pretrained=False, out_dim=6)).eval()
+    m.audio_encoder.config._attn_implementation = "eager"
+    with torch.no_grad():
+        for p in m.transformer_decoder.parameters():          # default init is near-identity: make the layers matter
+            if p.dim() > 1:
+                p.mul_(3.0)
+        audio = torch.randn(1, 16000)
+        want = m.infer(audio, T, id_seed=torch.tensor([7]))
+        got = kv_cached_infer(m, audio, T, id_seed=torch.tensor([7]))
+        enable_kv_cache(m)
+        again = m.infer(audio, T, id_seed=torch.tensor([7]))
+    assert got.shape == want.shape == (1, T, 6), (got.shape, want.shape)
+    assert torch.equal(got, again)
+    err = ((got - want).norm() / want.norm()).item()
+    spread = (want[0, 1:] - want[0, :-1]).abs().mean().item()
+    assert spread > 1e-3, "degenerate reference output: the test would prove nothing"
+    worst = max(worst, err)
+print("RESULT", worst)
+'''
+    r = subprocess.run([sys.executable, "-c", script, str(tmp_path), ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    worst = float([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][-1].split()[1])
+    print(f"kv-cached pose decoder vs reference re-decoding: rel-L2 {worst:.2e}")
+    assert worst < 1e-4
